@@ -1,0 +1,119 @@
+/* sdn.h - C ABI of libsdn_b200.so: the B200-native (sm_100a) stereo U-Net step.
+ *
+ * The reference (sdfgeoff/stereo_depth_estimation) is pure Python and has no
+ * FFI; the boundary it exposes for this hot path is the Python surface of
+ *   src/foundation_stereo_depth/model.py:48-104   (StereoUNet.forward)
+ *   src/foundation_stereo_depth/train.py:320-357  (loss + metric sums in run_epoch)
+ *   src/foundation_stereo_depth/dataset.py:23-30,184-270,302-311 (sample pipeline)
+ *   src/live_camera/depth_live_dl.py:516-529      (single-pair inference)
+ * Every entry point below names the reference interface it replaces.  The
+ * Python mirror (stereo_depth_estimation_b200/, ctypes) is the host side.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); all
+ * pointers are DEVICE pointers unless the name says host; every function
+ * returns 0 on success and a negative code on failure, with a thread-local
+ * message available from sdn_last_error().  Work is enqueued on the caller's
+ * CUDA stream (passed as void*, a cudaStream_t) and is asynchronous.  The
+ * library owns only its context/workspace; parameters, gradients, inputs and
+ * outputs stay owned by the caller (PyTorch storages in practice).
+ */
+#ifndef SDN_H_
+#define SDN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdn_ctx sdn_ctx;
+
+#define SDN_NUM_PARAMS 66 /* len(list(StereoUNet().parameters())), model.py:59-77 */
+#define SDN_NUM_BN 18     /* BatchNorm2d layers, model.py:37,40 (x9 blocks) */
+#define SDN_NUM_STAGES 4  /* backward stages == gradient all-reduce buckets */
+
+/* Per-view photometric augmentation parameters, the explicit form of the
+ * reference samplers dataset.py:214-246 consumed by dataset.py:248-270. */
+typedef struct sdn_aug_params {
+    float brightness;    /* _sample_jitter_factor(brightness_jitter) */
+    float contrast;      /* _sample_jitter_factor(contrast_jitter) */
+    float saturation;    /* _sample_jitter_factor(saturation_jitter) */
+    float hue;           /* _sample_hue_shift() */
+    float gamma;         /* _sample_gamma_factor() */
+    float blur_sigma;    /* > 0: gaussian_blur(k=5, sigma); 0: no blur (coin came up tails) */
+    float noise_std;     /* _sample_noise_std() */
+    uint32_t noise_seed; /* stream id of the device Philox generator */
+} sdn_aug_params;
+
+const char* sdn_last_error(void);
+int sdn_version(void);
+
+/* Context: workspace for batches up to max_batch at resolution H x W
+ * (both multiples of 16, model.py:79-95 pooling/upsampling constraint). */
+int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags);
+int sdn_destroy(sdn_ctx* ctx);
+/* Bytes of device workspace the context holds. */
+int64_t sdn_workspace_bytes(const sdn_ctx* ctx);
+
+/* Borrow the 66 fp32 parameter tensors in StereoUNet.parameters() order
+ * (model.py:59-77), optional gradient destinations (same order, same layouts,
+ * entries may be NULL), and the 18 BatchNorm running buffers in module order
+ * (state_dict keys *.running_mean / *.running_var / *.num_batches_tracked). */
+int sdn_set_params(sdn_ctx* ctx, const float* const* params, float* const* grads, float* const* bn_running_mean,
+                   float* const* bn_running_var, int64_t* const* bn_num_batches_tracked);
+
+/* StereoUNet.forward(x, return_uncertainty) (model.py:79-104).
+ * x: fp32 NCHW [B,6,H,W]; disp / logvar: fp32 [B,1,H,W] (logvar may be NULL).
+ * training != 0: BatchNorm uses batch statistics and updates the running
+ * buffers, activations are kept for sdn_backward*.  params_dirty != 0: the fp32
+ * parameters changed since the last call (repack the bf16 operand cache). */
+int sdn_forward(sdn_ctx* ctx, const float* x, float* disp, float* logvar, int B, int training, int params_dirty,
+                void* stream);
+
+/* autograd of forward (what loss.backward() at train.py:342 reaches): seeds with
+ * dL/d(disp), dL/d(logvar) (fp32 [B,1,H,W], g_logvar may be NULL) and runs the
+ * head backward.  Then sdn_backward_stage(s) for s = 0..SDN_NUM_STAGES-1 in
+ * order; when stage s has run, the gradients of the parameters in
+ * sdn_stage_param_range(s) are final in the caller's grad tensors. */
+int sdn_backward_begin(sdn_ctx* ctx, const float* g_disp, const float* g_logvar, int accumulate, void* stream);
+int sdn_backward_stage(sdn_ctx* ctx, int stage, void* stream);
+int sdn_stage_param_range(int stage, int* first_param, int* num_params);
+
+/* Fused heteroscedastic Laplace loss (train.py:329-357) on the forward just run:
+ * mask = valid_mask & isfinite(target); n = sum(mask) (device side);
+ * sums[0..3] += sum nll, sum |diff|, sum diff^2, sum exp(0.5*logvar) over mask,
+ * *count += n; seeds the backward with dL/dz for L = sum(nll)/n_norm where
+ * n_norm = *n_norm_dev (a device u64, e.g. the all-reduced global count) or n if
+ * NULL.  with_backward == 0 gives the validation path (metrics only).
+ * disp / logvar outputs are optional (NULL skips the store). */
+int sdn_loss_begin(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask, float* disp, float* logvar,
+                   float* sums4, unsigned long long* count, const unsigned long long* n_norm_dev, int with_backward,
+                   int accumulate, void* stream);
+/* n = sum(valid_mask & isfinite(target)) into *count_out (device u64, pre-zeroed by the callee). */
+int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask, int B, unsigned long long* count_out,
+                    void* stream);
+
+/* FoundationStereoDataset.__getitem__ + default collate (dataset.py:184-212,
+ * 248-270, 302-311) for a batch of raw uint8 HWC images already on the device:
+ * left / right RGB and the RGB-encoded disparity, each [B,Hs,Ws,3].
+ * Outputs: input fp32 [B,6,H,W], target fp32 [B,1,H,W], mask u8 [B,1,H,W],
+ * *valid_count (device u64, optional) = sum(mask & isfinite(target)).
+ * aug: 2*B parameter structs on the DEVICE (left, right per sample) or NULL for
+ * augment=False. */
+int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
+                   int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
+                   unsigned long long* valid_count, void* stream);
+
+/* Test / debug access to the NHWC bf16 activations of the last forward:
+ * which = conv layer index 0..17; kind 0 = pre-BN conv output, 1 = post
+ * BN+ReLU, 2 = gradient w.r.t. the pre-BN output (after backward).
+ * Copies to a host fp32 buffer of B*H_l*W_l*C_l elements; returns the dims. */
+int sdn_debug_read(sdn_ctx* ctx, int which, int kind, float* host_out, int64_t capacity, int* dims4);
+
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t sdn_launch_count(const sdn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDN_H_ */

@@ -1,0 +1,328 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel covers every "pixels x channels"
+// contraction of the stereo U-Net (reference model: src/foundation_stereo_depth/
+// model.py:32-104):
+//   * conv3x3 forward       (model.py:36,39)  : 9 (or 18, skip-concat) A-segments
+//   * conv3x3 data gradient                    : same, weights flipped/transposed
+//   * ConvTranspose2d 2x2/s2 forward (model.py:67-73): 1 segment, 4 strided D maps
+//   * ConvTranspose2d data gradient            : 4 segments over 4 strided A maps
+//   * the im2col'ed first layer (enc1.block.0) : 1 segment, K = 64
+//
+// GEMM view: D[M = 128 pixels, N = BLOCK_N channels] += A[M, K] * B[N, K]^T with
+// both operands K-major bf16 in shared memory (TMA, hardware swizzle) and the
+// fp32 accumulator in TMEM.  The A tile of one k-block is ONE 4-D TMA box
+// (channels, TW, TH, TN) of an NHWC activation tensor, shifted by the filter
+// tap; out-of-bounds rows/columns are zero-filled by TMA, which is exactly the
+// conv's zero padding.  torch.cat([up, skip]) (model.py:89-95) never
+// materialises: the K loop simply walks two tensor maps.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> bf16 -> swizzled smem ->
+// TMA store), double-buffered accumulators so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace sdn {
+
+enum : int { CG_RELU = 1, CG_STATS = 2 };
+
+struct CgSeg {
+    int8_t map;  // index into a_maps
+    int8_t dx;   // added to the tile's x0
+    int8_t dy;   // added to the tile's y0
+    int8_t pad_;
+    int16_t c0;       // first channel in that map
+    int16_t cblocks;  // k-blocks taken from this segment
+};
+
+constexpr int CG_MAX_SEGS = 18;
+
+struct alignas(64) ConvGemmParams {
+    CUtensorMap a_maps[4];
+    CUtensorMap b_map;
+    CUtensorMap d_maps[4];
+    CgSeg segs[CG_MAX_SEGS];
+    int nsegs;
+    int kblocks_total;
+    int tiles_x, tiles_y, tiles_n;  // M tiling of (W, H, batch)
+    int TW, TH, TN;                 // pixel box, TW*TH*TN == 128
+    int n_tiles;                    // N tiling
+    int n_tiles_per_dmap;           // N tiles that land in one D map
+    int n_total;                    // n_tiles * BLOCK_N
+    int flags;
+    int stages;
+    const float* bias;      // [n_total] or nullptr; added before ReLU
+    float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS
+};
+
+template <int SWA, int BLOCK_N>
+struct CgCfg {
+    static constexpr int KB = SWA / 2;  // bf16 channels per k-block
+    static constexpr int A_BYTES = 128 * SWA;
+    static constexpr int B_BYTES = BLOCK_N * SWA;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SWD = BLOCK_N >= 64 ? 128 : 64;  // staging / store swizzle
+    static constexpr int DCH = SWD / 2;                   // channels per D block
+    static constexpr int D_BLOCKS = BLOCK_N / DCH;
+    static constexpr int D_BLOCK_BYTES = 128 * SWD;
+    static constexpr int D_BYTES = 128 * BLOCK_N * 2;
+    static constexpr int WPR = DCH / 2;     // 32-bit words per staging row
+    static constexpr int RG = 128 / WPR;    // row groups in the stats pass
+    static constexpr int SCRATCH_BYTES = RG * BLOCK_N * 2 * 4;
+    static constexpr int ACC_BYTES = 2 * 512 * 4;
+    static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+    static constexpr int smem_bytes(int stages) {
+        return 1024 + stages * STAGE_BYTES + D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
+    }
+};
+
+template <int SWA, int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = CgCfg<SWA, BLOCK_N>;
+    constexpr int KB = Cfg::KB;
+    constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
+    constexpr uint32_t SBO_A = 8 * SWA;
+    constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BLOCK_N, 0, 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint8_t* stage_base = smem;
+    uint8_t* stg = smem + stages * Cfg::STAGE_BYTES;  // D staging, 1024-aligned
+    float* scratch = reinterpret_cast<float*>(stg + Cfg::D_BYTES);
+    float* acc_sum = reinterpret_cast<float*>(stg + Cfg::D_BYTES + Cfg::SCRATCH_BYTES);
+    float* acc_sq = acc_sum + 512;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::D_BYTES + Cfg::SCRATCH_BYTES + Cfg::ACC_BYTES);
+    uint64_t* full_bar = bars;         // [8]
+    uint64_t* empty_bar = bars + 8;    // [8]
+    uint64_t* tfull_bar = bars + 16;   // [2]
+    uint64_t* tempty_bar = bars + 18;  // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int num_tiles = m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tfull_bar[a], 1);
+            ptx::mbar_init(&tempty_bar[a], 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
+        ptx::prefetch_tmap(&p.b_map);
+        for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.d_maps[i]);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    if (threadIdx.x >= 64) {
+        for (int i = threadIdx.x - 64; i < 1024; i += 128) acc_sum[i] = 0.f;  // acc_sum and acc_sq are contiguous
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_tile = t % p.n_tiles;
+                const int m_tile = t / p.n_tiles;
+                const int tx = m_tile % p.tiles_x;
+                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+                const int tn = m_tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                int kcount = 0;
+                for (int sg = 0; sg < p.nsegs; ++sg) {
+                    const CgSeg seg = p.segs[sg];
+                    for (int cb = 0; cb < seg.cblocks; ++cb) {
+                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* a_dst = stage_base + s * Cfg::STAGE_BYTES;
+                        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                         y0 + seg.dy, n0);
+                        ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                        ++kcount;
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int a = 0;
+            uint32_t aph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + a * BLOCK_N;
+                for (int kb = 0; kb < p.kblocks_total; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    const uint64_t adesc = ptx::make_smem_desc(a_addr, 16, SBO_A, LAYOUT_A);
+                    const uint64_t bdesc = ptx::make_smem_desc(b_addr, 16, SBO_A, LAYOUT_A);
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k) {
+                        // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
+                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                         (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::tc_commit(&empty_bar[s]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                ptx::tc_commit(&tfull_bar[a]);
+                a ^= 1;
+                if (a == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int te = threadIdx.x - 64;     // 0..127
+        const int quarter = warp & 3;        // TMEM lane quarter this warp may read
+        const int r = quarter * 32 + lane;   // tile row == pixel index in the box
+        const bool do_stats = (p.flags & CG_STATS) != 0;
+        const bool do_relu = (p.flags & CG_RELU) != 0;
+        int a = 0;
+        uint32_t aph = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_tile = t % p.n_tiles;
+            const int m_tile = t / p.n_tiles;
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int tn = m_tile / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+
+            ptx::mbar_wait(&tfull_bar[a], aph);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BLOCK_N;
+#pragma unroll
+            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + ch * 32, v);
+                ptx::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+                    const float* b = p.bias + n_tile * BLOCK_N + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(b + j);
+                }
+                if (do_relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                const int cbk = (ch * 32) / Cfg::DCH;
+                const int j0 = ((ch * 32) % Cfg::DCH) / 8;
+                uint8_t* rowp = stg + cbk * Cfg::D_BLOCK_BYTES + r * Cfg::SWD;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 q;
+                    q.x = ptx::pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                    q.y = ptx::pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                    q.z = ptx::pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                    q.w = ptx::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                    const int sw = (Cfg::SWD == 128) ? ((j0 + i) ^ (r & 7)) : ((j0 + i) ^ ((r >> 1) & 3));
+                    *reinterpret_cast<uint4*>(rowp + (sw << 4)) = q;
+                }
+            }
+            // accumulator drained: hand the TMEM stage back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[a]);
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(1, 128);
+
+            if (te == 0) {
+                const int dmap = n_tile / p.n_tiles_per_dmap;
+                const int cbase = (n_tile % p.n_tiles_per_dmap) * BLOCK_N;
+#pragma unroll
+                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk)
+                    ptx::tma_store_4d(&p.d_maps[dmap], stg + cbk * Cfg::D_BLOCK_BYTES, cbase + cbk * Cfg::DCH, x0, y0,
+                                      n0);
+                ptx::tma_store_commit();
+            }
+            if (do_stats) {
+                // per-channel sum / sum of squares of the bf16 values just staged
+                // (== what the next kernel will read back), reduced over the 128 rows
+                const int w = te % Cfg::WPR;
+                const int rg = te / Cfg::WPR;
+                constexpr int ROWS = 128 / Cfg::RG;
+#pragma unroll
+                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    const uint8_t* blk = stg + cbk * Cfg::D_BLOCK_BYTES;
+#pragma unroll 4
+                    for (int rr = 0; rr < ROWS; ++rr) {
+                        const int row = rg * ROWS + rr;
+                        const int j = w >> 2;
+                        const int sw = (Cfg::SWD == 128) ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3));
+                        const uint32_t u =
+                            *reinterpret_cast<const uint32_t*>(blk + row * Cfg::SWD + (sw << 4) + ((w & 3) << 2));
+                        const float lo = __uint_as_float(u << 16);
+                        const float hi = __uint_as_float(u & 0xFFFF0000u);
+                        s0 += lo; q0 = fmaf(lo, lo, q0);
+                        s1 += hi; q1 = fmaf(hi, hi, q1);
+                    }
+                    const int chn = cbk * Cfg::DCH + 2 * w;
+                    scratch[rg * BLOCK_N + chn] = s0;
+                    scratch[rg * BLOCK_N + chn + 1] = s1;
+                    scratch[Cfg::RG * BLOCK_N + rg * BLOCK_N + chn] = q0;
+                    scratch[Cfg::RG * BLOCK_N + rg * BLOCK_N + chn + 1] = q1;
+                }
+                ptx::named_bar_sync(2, 128);
+                for (int c = te; c < BLOCK_N; c += 128) {
+                    float s = 0.f, q = 0.f;
+#pragma unroll
+                    for (int g = 0; g < Cfg::RG; ++g) {
+                        s += scratch[g * BLOCK_N + c];
+                        q += scratch[Cfg::RG * BLOCK_N + g * BLOCK_N + c];
+                    }
+                    acc_sum[n_tile * BLOCK_N + c] += s;
+                    acc_sq[n_tile * BLOCK_N + c] += q;
+                }
+            }
+            if (te == 0) ptx::tma_store_wait_read0();
+            ptx::named_bar_sync(1, 128);
+            a ^= 1;
+            if (a == 0) aph ^= 1;
+        }
+        if (do_stats) {
+            float* dst = p.stats_partials + size_t(blockIdx.x) * 2 * p.n_total;
+            for (int c = te; c < p.n_total; c += 128) {
+                dst[c] = acc_sum[c];
+                dst[p.n_total + c] = acc_sq[c];
+            }
+        }
+        if (te == 0) ptx::tma_store_wait0();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace sdn

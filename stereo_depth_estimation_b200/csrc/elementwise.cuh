@@ -1,0 +1,578 @@
+// Memory-bound kernels around the tensor-core convolutions: weight packing,
+// first-layer im2col, BatchNorm (train statistics / eval), ReLU, MaxPool, the
+// two 1x1 heads with softplus / clamp, the heteroscedastic Laplace loss and the
+// backward counterparts.  All activations are NHWC bf16; every kernel moves
+// 16-byte vectors (8 channels) per thread and is sized as a grid-stride loop
+// over a multiple of the SM count.
+//
+// Reference semantics (cited per kernel):
+//   ConvBlock conv->BN->ReLU x2 : src/foundation_stereo_depth/model.py:32-45
+//   MaxPool2d(2)                : model.py:59,83-86
+//   heads, softplus, clamp      : model.py:76-77,98,103
+//   loss + metric sums          : src/foundation_stereo_depth/train.py:329-357
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdn {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(u[i] << 16);
+        f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 q;
+    q.x = pack2(f[0], f[1]);
+    q.y = pack2(f[2], f[3]);
+    q.z = pack2(f[4], f[5]);
+    q.w = pack2(f[6], f[7]);
+    return q;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ------------------------------------------------------------------ packing
+// mode 0: conv3x3 forward   dst[co][tap*Ci + ci]          = W[co][ci][tap]
+// mode 1: conv3x3 dgrad     dst[ci][tap*Co + co]          = W[co][ci][8 - tap]
+// mode 2: first layer       dst[co][k], k = tap*Ci + ci<54 = W[co][ci][tap], zero-padded to Kpad
+// mode 3: convT forward     dst[(q*Co + co)][ci]          = W[ci][co][q]      (W is [Ci][Co][2][2])
+// mode 4: convT dgrad       dst[ci][q*Co + co]            = W[ci][co][q]
+__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int mode, int Co, int Ci,
+                                   int Kpad) {
+    const int total = (mode == 2) ? Co * Kpad : (mode >= 3 ? 4 * Co * Ci : 9 * Co * Ci);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (mode == 0) {
+            const int co = i / (9 * Ci), rem = i % (9 * Ci), tap = rem / Ci, ci = rem % Ci;
+            v = w[(co * Ci + ci) * 9 + tap];
+        } else if (mode == 1) {
+            const int ci = i / (9 * Co), rem = i % (9 * Co), tap = rem / Co, co = rem % Co;
+            v = w[(co * Ci + ci) * 9 + (8 - tap)];
+        } else if (mode == 2) {
+            const int co = i / Kpad, k = i % Kpad;
+            if (k < 9 * Ci) {
+                const int tap = k / Ci, ci = k % Ci;
+                v = w[(co * Ci + ci) * 9 + tap];
+            }
+        } else if (mode == 3) {
+            const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
+            v = w[(ci * Co + co) * 4 + q];
+        } else {
+            const int ci = i / (4 * Co), rem = i % (4 * Co), q = rem / Co, co = rem % Co;
+            v = w[(ci * Co + co) * 4 + q];
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// bias replicated over the 4 quadrants of a ConvTranspose2d GEMM: dst[q*Co + co] = b[co]
+__global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int Co, int reps) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Co * reps; i += gridDim.x * blockDim.x) dst[i] = b[i % Co];
+}
+
+// ------------------------------------------------------- first-layer im2col
+// x fp32 NCHW [B,Cin,H,W] (the reference sample layout, dataset.py:305-311) ->
+// bf16 [B,H,W,64] with k = (dy*3+dx)*Cin + c, zero padding at the border and
+// zeros for k >= 9*Cin.  One thread = 8 consecutive k of one pixel (16-byte store).
+__global__ void im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H,
+                                    int W) {
+    const long long total = (long long)B * H * W * 8;
+    const int K = 9 * Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = int(i & 7);
+        const long long pix = i >> 3;
+        const int xw = int(pix % W);
+        const int yh = int((pix / W) % H);
+        const int n = int(pix / ((long long)W * H));
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float v = 0.f;
+            if (k < K) {
+                const int tap = k / Cin, c = k % Cin;
+                const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((long long)n * Cin + c) * H + yy) * W + xx);
+            }
+            f[j] = v;
+        }
+        *reinterpret_cast<uint4*>(out + pix * 64 + g * 8) = pack8(f);
+    }
+}
+
+// -------------------------------------------------------------- BatchNorm
+// Training statistics (nn.BatchNorm2d in train mode, model.py:37,40): biased
+// variance for normalisation, unbiased into running_var, momentum 0.1,
+// num_batches_tracked += 1.  partials = per-CTA (sum, sumsq) rows written by the
+// conv epilogue; summed here in fp64 in a fixed order (deterministic).
+__global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         long long* __restrict__ num_batches, float eps, float momentum,
+                                         float* __restrict__ scale, float* __restrict__ shift,
+                                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches != nullptr) *num_batches += 1;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+        s += (double)partials[(size_t)i * 2 * C + c];
+        q += (double)partials[(size_t)i * 2 * C + C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    mean_out[c] = (float)mean;
+    rstd_out[c] = rstd;
+    if (running_mean != nullptr) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// Eval mode: normalise with the running statistics.
+__global__ void bn_prepare_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                       float eps, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = 1.f / sqrtf(running_var[c] + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - running_mean[c] * sc;
+}
+
+// a = relu(y*scale + shift), optionally also p = maxpool2x2(a).
+// POOL: one thread = a 2x2 pixel quad x 8 channels.  Otherwise one pixel x 8 channels.
+template <bool POOL>
+__global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, bf16* __restrict__ a, bf16* __restrict__ pooled,
+                                    int B, int H, int W, int C) {
+    const int CG = C >> 3;
+    if (POOL) {
+        const int H2 = H >> 1, W2 = W >> 1;
+        const long long total = (long long)B * H2 * W2 * CG;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int cg = int(i % CG);
+            const long long qd = i / CG;
+            const int x2 = int(qd % W2);
+            const int y2 = int((qd / W2) % H2);
+            const int n = int(qd / ((long long)W2 * H2));
+            float sc[8], sh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cg * 8 + j); sh[j] = __ldg(shift + cg * 8 + j); }
+            float mx[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mx[j] = 0.f;  // relu output >= 0
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const long long pix = ((long long)n * H + (2 * y2 + (d >> 1))) * W + (2 * x2 + (d & 1));
+                float f[8];
+                unpack8(ldg16(y + pix * C + cg * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                }
+                const uint4 o = pack8(f);
+                *reinterpret_cast<uint4*>(a + pix * C + cg * 8) = o;
+                float g[8];
+                unpack8(o, g);  // pool the bf16-rounded values (what the consumers will see)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], g[j]);
+            }
+            *reinterpret_cast<uint4*>(pooled + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8) = pack8(mx);
+        }
+    } else {
+        const long long total = (long long)B * H * W * CG;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int cg = int(i % CG);
+            float f[8];
+            unpack8(ldg16(y + i * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                f[j] = fmaxf(fmaf(f[j], __ldg(scale + cg * 8 + j), __ldg(shift + cg * 8 + j)), 0.f);
+            *reinterpret_cast<uint4*>(a + i * 8) = pack8(f);
+        }
+    }
+}
+
+// ---------------------------------------------------- BatchNorm+ReLU backward
+// Inputs: y (pre-BN conv output), g (gradient w.r.t. the block's ReLU output,
+// full resolution) and optionally gp (gradient w.r.t. the 2x2-max-pooled
+// output, half resolution) which is routed to the first maximum of each quad in
+// row-major order (nn.MaxPool2d backward, model.py:59).  dz = relu'(z) * dA.
+// Pass 1 (reduce): per-channel sum(dz), sum(dz * xhat)  -> per-block partials.
+// Pass 2 (apply) : dy = scale * (dz - c1 - xhat * c2)  with c1 = sum(dz)/M,
+//                  c2 = sum(dz*xhat)/M (training mode batch-norm backward).
+struct BnBwdQuad {
+    float dz[4][8];
+    float xh[4][8];
+};
+
+template <bool POOL>
+__device__ __forceinline__ void bn_bwd_load(const bf16* __restrict__ y, const bf16* __restrict__ g,
+                                            const bf16* __restrict__ gp, const float* sc, const float* sh,
+                                            const float* mu, const float* rs, long long i, int B, int H, int W, int C,
+                                            BnBwdQuad& o, long long (&pix)[4]) {
+    const int CG = C >> 3;
+    const int cg = int(i % CG);
+    if (POOL) {
+        const int H2 = H >> 1, W2 = W >> 1;
+        const long long qd = i / CG;
+        const int x2 = int(qd % W2);
+        const int y2 = int((qd / W2) % H2);
+        const int n = int(qd / ((long long)W2 * H2));
+        float gpf[8];
+        unpack8(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gpf);
+        float z[4][8], ab[4][8];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            pix[d] = ((long long)n * H + (2 * y2 + (d >> 1))) * W + (2 * x2 + (d & 1));
+            float yf[8], gf[8];
+            unpack8(ldg16(y + pix[d] * C + cg * 8), yf);
+            unpack8(ldg16(g + pix[d] * C + cg * 8), gf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                z[d][j] = fmaf(yf[j], sc[j], sh[j]);
+                // the forward pooled the bf16-rounded activation: reproduce it for the arg-max
+                ab[d][j] = __bfloat162float(__float2bfloat16_rn(fmaxf(z[d][j], 0.f)));
+                o.xh[d][j] = (yf[j] - mu[j]) * rs[j];
+                o.dz[d][j] = gf[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int am = 0;
+            float best = ab[0][j];
+#pragma unroll
+            for (int d = 1; d < 4; ++d)
+                if (ab[d][j] > best) { best = ab[d][j]; am = d; }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                float da = o.dz[d][j] + (d == am ? gpf[j] : 0.f);
+                o.dz[d][j] = z[d][j] > 0.f ? da : 0.f;
+            }
+        }
+    } else {
+        pix[0] = i / CG;
+        float yf[8], gf[8];
+        unpack8(ldg16(y + i * 8), yf);
+        unpack8(ldg16(g + i * 8), gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(yf[j], sc[j], sh[j]);
+            o.xh[0][j] = (yf[j] - mu[j]) * rs[j];
+            o.dz[0][j] = z > 0.f ? gf[j] : 0.f;
+        }
+    }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
+                                                            const bf16* __restrict__ gp,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            float* __restrict__ partials, int B, int H, int W, int C) {
+    const int CG = C >> 3;
+    const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
+    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = int(tid0 % CG);  // fixed per thread: the stride is a multiple of CG
+    float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x) {
+        BnBwdQuad q;
+        long long pix[4];
+        bn_bwd_load<POOL>(y, g, gp, sc, sh, mu, rs, i, B, H, W, C, q, pix);
+#pragma unroll
+        for (int d = 0; d < (POOL ? 4 : 1); ++d)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += q.dz[d][j];
+                s2[j] = fmaf(q.dz[d][j], q.xh[d][j], s2[j]);
+            }
+    }
+    __shared__ float red[256][17];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
+    __syncthreads();
+    // thread t < 2*C reduces one (sum kind, channel) over the threads that share its channel group
+    for (int o = threadIdx.x; o < 2 * C; o += blockDim.x) {
+        const int kind = o / C, c = o % C, g8 = c >> 3, j = c & 7;
+        float acc = 0.f;
+        for (int t = g8; t < (int)blockDim.x; t += CG) acc += red[t][kind * 8 + j];
+        partials[(size_t)blockIdx.x * 2 * C + o] = acc;
+    }
+}
+
+// partials -> c1, c2 and the affine parameter gradients (dgamma = sum(dz*xhat), dbeta = sum(dz)).
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                       float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+        s1 += (double)partials[(size_t)i * 2 * C + c];
+        s2 += (double)partials[(size_t)i * 2 * C + C + c];
+    }
+    c1[c] = (float)(s1 / count);
+    c2[c] = (float)(s2 / count);
+    if (dgamma != nullptr) {
+        if (accumulate) { dgamma[c] += (float)s2; dbeta[c] += (float)s1; }
+        else { dgamma[c] = (float)s2; dbeta[c] = (float)s1; }
+    }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
+                                                           const bf16* __restrict__ gp,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const float* __restrict__ c1, const float* __restrict__ c2,
+                                                           bf16* __restrict__ dy, int B, int H, int W, int C) {
+    const int CG = C >> 3;
+    const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
+    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = int(tid0 % CG);
+    float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
+        k1[j] = c1[cg * 8 + j]; k2[j] = c2[cg * 8 + j];
+    }
+    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x) {
+        BnBwdQuad q;
+        long long pix[4];
+        bn_bwd_load<POOL>(y, g, gp, sc, sh, mu, rs, i, B, H, W, C, q, pix);
+#pragma unroll
+        for (int d = 0; d < (POOL ? 4 : 1); ++d) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = sc[j] * (q.dz[d][j] - k1[j] - q.xh[d][j] * k2[j]);
+            *reinterpret_cast<uint4*>(dy + pix[d] * C + cg * 8) = pack8(o);
+        }
+    }
+}
+
+// Per-channel column sum of an NHWC bf16 tensor (ConvTranspose2d bias gradient).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long npix, int C,
+                                                     float* __restrict__ out, int accumulate) {
+    // one block per 8-channel group slice; grid.x = C/8, grid.y = slices (atomics merge slices)
+    const int cg = blockIdx.x;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (long long p = (long long)blockIdx.y * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.y * blockDim.x) {
+        float f[8];
+        unpack8(ldg16(x + p * C + cg * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+    __shared__ float red[8][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = s[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(out + cg * 8 + threadIdx.x, v);
+    }
+    (void)accumulate;
+}
+
+// ------------------------------------------------------------ heads + loss
+// z_d = w_d . d1 + b_d ; disparity = softplus(z_d)        (model.py:76,98)
+// z_l = w_l . d1 + b_l ; logvar    = clamp(z_l, -6, 3)    (model.py:77,103)
+// MODE 0: forward only.
+// MODE 1: backward with external output gradients g_disp / g_logvar (the
+//         nn.Module drop-in path: the loss lives in train.py:329-340).
+// MODE 2: fused heteroscedastic Laplace loss (train.py:329-357): forward,
+//         5 metric sums, and the loss gradient seeded with 1/n, n read from device.
+// sums layout (fp32, atomically accumulated, pre-zeroed by the caller):
+//   [0] sum nll  [1] sum |diff|  [2] sum diff^2  [3] sum exp(0.5*logvar); the valid count is a separate u64
+// head_grads layout: [0,32) dW_d  [32] db_d  [33,65) dW_l  [65] db_l
+template <int MODE>
+__global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, const float* __restrict__ w_d,
+                                                   const float* __restrict__ b_d, const float* __restrict__ w_l,
+                                                   const float* __restrict__ b_l, float* __restrict__ disp,
+                                                   float* __restrict__ logvar, const float* __restrict__ g_disp,
+                                                   const float* __restrict__ g_logvar,
+                                                   const float* __restrict__ target,
+                                                   const uint8_t* __restrict__ mask,
+                                                   const unsigned long long* __restrict__ n_valid,
+                                                   float* __restrict__ sums,
+                                                   unsigned long long* __restrict__ count_out,
+                                                   bf16* __restrict__ g_d1, float* __restrict__ head_grads,
+                                                   long long npix) {
+    __shared__ float swd[32], swl[32];
+    __shared__ float red[8][72];
+    if (threadIdx.x < 32) { swd[threadIdx.x] = w_d[threadIdx.x]; swl[threadIdx.x] = w_l[threadIdx.x]; }
+    __syncthreads();
+    const float bd = b_d[0], bl = b_l[0];
+    float inv_n = 0.f;
+    if (MODE == 2) {
+        const unsigned long long n = n_valid[0];
+        inv_n = n > 0ull ? 1.f / (float)n : 0.f;
+    }
+    float acc[72];
+    if (MODE != 0) {
+#pragma unroll
+        for (int j = 0; j < 72; ++j) acc[j] = 0.f;
+    }
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+         p += (long long)gridDim.x * blockDim.x) {
+        float f[32];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float t8[8];
+            unpack8(ldg16(d1 + p * 32 + v * 8), t8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[v * 8 + j] = t8[j];
+        }
+        float zd = bd, zl = bl;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { zd = fmaf(f[j], swd[j], zd); zl = fmaf(f[j], swl[j], zl); }
+        const float dsp = zd > 20.f ? zd : log1pf(expf(zd));
+        const float lv = fminf(fmaxf(zl, -6.f), 3.f);
+        if (MODE != 1) {
+            if (disp != nullptr) disp[p] = dsp;
+            if (logvar != nullptr) logvar[p] = lv;
+        }
+        if (MODE == 0) continue;
+        float gd, gl;
+        if (MODE == 1) {
+            gd = g_disp[p];
+            gl = g_logvar != nullptr ? g_logvar[p] : 0.f;
+        } else {
+            const float tg = target[p];
+            const bool m = (mask[p] != 0) && isfinite(tg);
+            gd = 0.f; gl = 0.f;
+            if (m) {
+                const float diff = dsp - tg;
+                const float ad = fabsf(diff);
+                const float e = expf(-lv);
+                const float nll = ad * e + lv;
+                acc[66] += nll;
+                acc[67] += ad;
+                acc[68] = fmaf(diff, diff, acc[68]);
+                acc[69] += expf(0.5f * lv);
+                acc[70] += 1.f;
+                const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                gd = sg * e * inv_n;
+                gl = (1.f - ad * e) * inv_n;
+            }
+        }
+        const float sig = zd > 20.f ? 1.f : 1.f / (1.f + expf(-zd));
+        const float dzd = gd * sig;
+        const float dzl = (zl >= -6.f && zl <= 3.f) ? gl : 0.f;
+        float o[8];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(dzd, swd[v * 8 + j], dzl * swl[v * 8 + j]);
+            *reinterpret_cast<uint4*>(g_d1 + p * 32 + v * 8) = pack8(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { acc[j] = fmaf(dzd, f[j], acc[j]); acc[33 + j] = fmaf(dzl, f[j], acc[33 + j]); }
+        acc[32] += dzd;
+        acc[65] += dzl;
+    }
+    if (MODE == 0) return;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 71; ++j) {
+        float v = acc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wrp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 71) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        if (threadIdx.x < 66) atomicAdd(head_grads + threadIdx.x, v);
+        else if (MODE == 2) {
+            if (threadIdx.x < 70) atomicAdd(sums + (threadIdx.x - 66), v);
+            else atomicAdd(count_out, (unsigned long long)v);  // block partial < 2^24: exact
+        }
+    }
+}
+
+// n = number of pixels with valid_mask & isfinite(target) (train.py:329-330), as a u64 on device.
+__global__ void __launch_bounds__(256) mask_count_kernel(const float* __restrict__ target,
+                                                         const uint8_t* __restrict__ mask, long long npix,
+                                                         unsigned long long* __restrict__ n_out) {
+    unsigned int c = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+         p += (long long)gridDim.x * blockDim.x)
+        c += (mask[p] != 0 && isfinite(target[p])) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ unsigned int red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(n_out, (unsigned long long)t);
+    }
+}
+
+// ------------------------------------------------------------- grad unpack
+// workspace layouts (written by wgrad_gemm_kernel) -> torch parameter layouts.
+// mode 0: conv3x3   ws[(tap*Ci + ci)][Co]  -> grad[Co][Ci][3][3]
+// mode 2: first     ws[k][Co], k=tap*Ci+ci -> grad[Co][Ci][3][3]   (same formula, ws has >= 9*Ci rows)
+// mode 3: convT     ws[q][ci][Co]          -> grad[Ci][Co][2][2]
+__global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int mode, int Co, int Ci,
+                                   int accumulate) {
+    const int total = (mode == 3) ? 4 * Co * Ci : 9 * Co * Ci;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v;
+        if (mode == 3) {
+            const int ci = i / (Co * 4), rem = i % (Co * 4), co = rem / 4, q = rem % 4;
+            v = ws[((size_t)q * Ci + ci) * Co + co];
+        } else {
+            const int co = i / (Ci * 9), rem = i % (Ci * 9), ci = rem / 9, tap = rem % 9;
+            v = ws[((size_t)tap * Ci + ci) * Co + co];
+        }
+        if (accumulate) grad[i] += v; else grad[i] = v;
+    }
+}
+
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int accumulate) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (accumulate) dst[i] += src[i]; else dst[i] = src[i];
+    }
+}
+
+}  // namespace sdn

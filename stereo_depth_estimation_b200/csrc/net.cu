@@ -1,0 +1,1001 @@
+// Host-side executor of the B200-native stereo U-Net step and its C ABI
+// (include/sdn.h).  It owns the layer plan, the TMA tensor maps, the bf16
+// operand cache and the activation workspace; it launches only the kernels in
+// conv_gemm.cuh / wgrad_gemm.cuh / elementwise.cuh / preprocess.cuh.  There is
+// no library GEMM/conv call and no CPU fallback anywhere on this path.
+//
+// Topology mirrored (not copied) from the reference model
+// src/foundation_stereo_depth/model.py:48-104:
+//   enc1..enc4, bottleneck, (up4,dec4) .. (up1,dec1), disparity/logvar heads.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdn.h"
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "preprocess.cuh"
+#include "wgrad_gemm.cuh"
+
+using namespace sdn;
+
+static_assert(sizeof(sdn_aug_params) == sizeof(AugParams), "ABI struct mismatch");
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define SDN_OK(call)              \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != 0) return r_;   \
+    } while (0)
+
+// ------------------------------------------------------- tensor-map encode
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+static CUtensorMapSwizzle swz(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                   : bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// 4-D bf16 map over (C, W, H, N) with explicit element strides for W, H, N.
+static int encode4(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH,
+                   long long sN, int bC, int bW, int bH, int bN, int swizzle_bytes) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bC, (cuuint32_t)bW, (cuuint32_t)bH, (cuuint32_t)bN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail("cuTensorMapEncodeTiled(4d) failed: %d (C=%d W=%d H=%d N=%d box=%d,%d,%d,%d sw=%d)", (int)r, C, W,
+                    H, N, bC, bW, bH, bN, swizzle_bytes);
+    return 0;
+}
+static int encode2(CUtensorMap* m, const void* base, int K, int Nrows, int bK, int bN, int swizzle_bytes) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bK, (cuuint32_t)bN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail("cuTensorMapEncodeTiled(2d) failed: %d (K=%d N=%d box=%d,%d sw=%d)", (int)r, K, Nrows, bK, bN,
+                    swizzle_bytes);
+    return 0;
+}
+
+// ------------------------------------------------------------- tile shapes
+struct Tile {
+    int TW, TH, TN;
+};
+// Pixel box (TW x TH x TN images) with TW*TH*TN == target that wastes the least
+// work on ragged edges; ties -> fewer images per box, then the squarest box.
+static Tile choose_tile(int W, int H, int B, int target) {
+    Tile best{target, 1, 1};
+    double best_cost = 1e300;
+    for (int TN = 1; TN <= target; TN *= 2)
+        for (int TW = 2; TW * TN <= target; TW *= 2) {
+            const int TH = target / (TW * TN);
+            if (TH < 1 || TW * TH * TN != target) continue;
+            if (TW > 256 || TH > 256) continue;
+            const double padded = double((W + TW - 1) / TW * TW) * double((H + TH - 1) / TH * TH) *
+                                  double((B + TN - 1) / TN * TN);
+            const double cost = padded * 1e6 + TN * 1e3 + double((TW + 2) * (TH + 2));
+            if (cost < best_cost) { best_cost = cost; best = Tile{TW, TH, TN}; }
+        }
+    return best;
+}
+
+// --------------------------------------------------------------- tensors
+struct Act {
+    bf16* p = nullptr;
+    int C = 0, H = 0, W = 0;  // per image; batch is the context's current B
+    size_t elems(int B) const { return (size_t)B * H * W * C; }
+};
+
+struct GemmOp {
+    ConvGemmParams p;
+    int swa = 128, block_n = 32, grid = 1, smem = 0;
+};
+struct WgradOp {
+    WgradParams p;
+    int swb = 128, smem = 0;
+    dim3 grid;
+};
+
+struct ConvL {  // conv3x3 + BatchNorm + ReLU
+    int cin = 0, cout = 0, lvl = 0;
+    int nsrc = 1;
+    const Act* src[2] = {nullptr, nullptr};
+    bool pooled_out = false;   // block output that is also max-pooled
+    bool first = false;        // enc1.block.0: im2col input, K = 64
+    int p_w = 0, p_gamma = 0, p_beta = 0, bn = 0;
+    Act y, a, pool, dy, ga, gp;
+    bf16 *wf = nullptr, *wd = nullptr;
+    float *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr, *c1 = nullptr, *c2 = nullptr;
+    float* wg = nullptr;  // fp32 weight-gradient workspace [9*cin][cout]
+    GemmOp fprop, dgrad;
+    WgradOp wgrad;
+    bool has_dgrad = true;
+};
+struct UpL {  // ConvTranspose2d(k=2, s=2)
+    int cin = 0, cout = 0, lvl_in = 0;
+    const Act* src = nullptr;
+    int src_layer = 0;
+    int p_w = 0, p_b = 0;
+    Act u, gu;
+    bf16 *wf = nullptr, *wd = nullptr;
+    float* bias4 = nullptr;
+    float* wg = nullptr;  // [4][cin][cout]
+    float* bg = nullptr;  // [cout]
+    GemmOp fprop, dgrad;
+    WgradOp wgrad;
+};
+
+struct sdn_ctx {
+    int device = 0, maxB = 0, H = 0, W = 0, num_sms = 148;
+    int B = 0;  // batch the tensor maps are currently encoded for
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    ConvL conv[18];
+    UpL up[4];
+    Act x0;     // im2col of the network input [B,H,W,64]
+    float* stats_partials = nullptr;  // [num_sms][2*512]
+    float* bwd_partials = nullptr;    // [BWD_BLOCKS][2*512]
+    float* head_grads = nullptr;      // 66 floats
+    float* wg_all = nullptr;          // all weight-gradient workspaces, contiguous
+    size_t wg_all_bytes = 0;
+    unsigned long long* n_local = nullptr;  // device u64
+    float* gray_part = nullptr;
+    float* blur_tmp = nullptr;
+    size_t blur_tmp_elems = 0;
+    const float* params[SDN_NUM_PARAMS] = {};
+    float* grads[SDN_NUM_PARAMS] = {};
+    float* bn_rm[SDN_NUM_BN] = {};
+    float* bn_rv[SDN_NUM_BN] = {};
+    int64_t* bn_nbt[SDN_NUM_BN] = {};
+    bool have_params = false, have_forward_train = false;
+    int accumulate = 0;
+    int64_t launches = 0;
+};
+
+static const int BWD_BLOCKS = 592;  // 4 x 148
+
+// level geometry
+static inline int lvl_h(const sdn_ctx* c, int lvl) { return c->H >> (lvl - 1); }
+static inline int lvl_w(const sdn_ctx* c, int lvl) { return c->W >> (lvl - 1); }
+
+// -------------------------------------------------------------- launchers
+template <int SWA, int BN>
+static int launch_cg_t(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    conv_gemm_kernel<SWA, BN><<<op.grid, 192, op.smem, st>>>(op.p);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    if (op.swa == 128) {
+        switch (op.block_n) {
+            case 32: return launch_cg_t<128, 32>(c, op, st);
+            case 64: return launch_cg_t<128, 64>(c, op, st);
+            case 128: return launch_cg_t<128, 128>(c, op, st);
+            case 256: return launch_cg_t<128, 256>(c, op, st);
+        }
+    } else if (op.swa == 64) {
+        switch (op.block_n) {
+            case 32: return launch_cg_t<64, 32>(c, op, st);
+            case 64: return launch_cg_t<64, 64>(c, op, st);
+        }
+    }
+    return fail("no conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
+}
+static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
+    if (op.swb == 128) wgrad_gemm_kernel<128><<<op.grid, 192, op.smem, st>>>(op.p);
+    else wgrad_gemm_kernel<64><<<op.grid, 192, op.smem, st>>>(op.p);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int set_smem_attrs() {
+    const int big = 227 * 1024;
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    return 0;
+}
+
+static int cg_smem(int swa, int bn, int stages) {
+    if (swa == 128) {
+        if (bn == 32) return CgCfg<128, 32>::smem_bytes(stages);
+        if (bn == 64) return CgCfg<128, 64>::smem_bytes(stages);
+        if (bn == 128) return CgCfg<128, 128>::smem_bytes(stages);
+        return CgCfg<128, 256>::smem_bytes(stages);
+    }
+    if (bn == 32) return CgCfg<64, 32>::smem_bytes(stages);
+    return CgCfg<64, 64>::smem_bytes(stages);
+}
+
+// Source description for one GEMM A-segment group: an activation tensor (or a
+// strided view of one) restricted to channels [c_off, c_off + C).
+struct SrcView {
+    const bf16* base;   // already offset to the view's first element
+    int C;              // channels in the view
+    int W, H;           // logical extent of the view
+    long long sW, sH, sN;  // element strides
+};
+static SrcView full_view(const Act& a, int c_off = 0, int C = -1) {
+    SrcView v;
+    v.base = a.p + c_off;
+    v.C = C < 0 ? a.C : C;
+    v.W = a.W; v.H = a.H;
+    v.sW = a.C; v.sH = (long long)a.W * a.C; v.sN = (long long)a.H * a.W * a.C;
+    return v;
+}
+// quadrant (i, j) of a 2x-upsampled tensor u[B, 2h, 2w, C], seen at the low resolution
+static SrcView quad_view(const Act& u, int q) {
+    const int i = q >> 1, j = q & 1;
+    SrcView v;
+    v.base = u.p + ((long long)i * u.W + j) * u.C;
+    v.C = u.C;
+    v.W = u.W / 2; v.H = u.H / 2;
+    v.sW = 2LL * u.C; v.sH = 2LL * u.W * u.C; v.sN = (long long)u.H * u.W * u.C;
+    return v;
+}
+
+// Fill a GemmOp.  segs: list of (view index, dx, dy); every view contributes all
+// of its channels per segment.  dviews: destination views, each n_per_dmap wide.
+struct SegSpec {
+    int view, dx, dy;
+};
+static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
+                      const std::vector<SegSpec>& segs, const bf16* bmat, int n_total,
+                      const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
+                      float* stats_partials) {
+    if (aviews.empty() || aviews.size() > 4 || dviews.empty() || dviews.size() > 4 || segs.size() > CG_MAX_SEGS)
+        return fail("build_gemm: bad view/segment counts");
+    memset(&op.p, 0, sizeof op.p);
+    bool all64 = true;
+    for (const SrcView& v : aviews) {
+        if (v.C % 32 != 0) return fail("build_gemm: source channels %d not a multiple of 32", v.C);
+        if (v.C % 64 != 0) all64 = false;
+    }
+    op.swa = all64 ? 128 : 64;
+    const int KB = op.swa / 2;
+    int bn = std::min(n_per_dmap, 256);
+    if (op.swa == 64 && bn > 64) bn = 64;
+    if (n_per_dmap % bn != 0) return fail("build_gemm: N %d not divisible by BLOCK_N %d", n_per_dmap, bn);
+    op.block_n = bn;
+    const int W = dviews[0].W, H = dviews[0].H;
+    const Tile t = choose_tile(W, H, B, 128);
+    ConvGemmParams& p = op.p;
+    p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
+    p.tiles_x = (W + t.TW - 1) / t.TW;
+    p.tiles_y = (H + t.TH - 1) / t.TH;
+    p.tiles_n = (B + t.TN - 1) / t.TN;
+    for (size_t i = 0; i < aviews.size(); ++i) {
+        const SrcView& v = aviews[i];
+        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, t.TW, t.TH, t.TN, op.swa));
+    }
+    for (size_t i = aviews.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    int kblocks = 0;
+    p.nsegs = (int)segs.size();
+    for (size_t s = 0; s < segs.size(); ++s) {
+        CgSeg& g = p.segs[s];
+        g.map = (int8_t)segs[s].view;
+        g.dx = (int8_t)segs[s].dx;
+        g.dy = (int8_t)segs[s].dy;
+        g.c0 = 0;
+        g.cblocks = (int16_t)(aviews[segs[s].view].C / KB);
+        kblocks += g.cblocks;
+    }
+    p.kblocks_total = kblocks;
+    SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
+    const int swd = bn >= 64 ? 128 : 64;
+    const int dch = swd / 2;
+    for (size_t i = 0; i < dviews.size(); ++i) {
+        const SrcView& v = dviews[i];
+        SDN_OK(encode4(&p.d_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, dch, t.TW, t.TH, t.TN, swd));
+    }
+    for (size_t i = dviews.size(); i < 4; ++i) p.d_maps[i] = p.d_maps[0];
+    p.n_tiles = n_total / bn;
+    p.n_tiles_per_dmap = n_per_dmap / bn;
+    p.n_total = n_total;
+    p.flags = flags;
+    p.bias = bias;
+    p.stats_partials = stats_partials;
+    if ((flags & CG_STATS) && n_total > 512) return fail("build_gemm: stats need n_total <= 512");
+    int stages = 8;
+    while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
+    p.stages = stages;
+    op.smem = cg_smem(op.swa, bn, stages);
+    const int num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
+    op.grid = std::max(1, std::min(num_tiles, c->num_sms));
+    return 0;
+}
+
+// Weight-gradient op.  avariants: dY views (1, or the 4 quadrants for convT);
+// bsrc: 1 or 2 X sources; taps 9 or 1.
+static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView>& avariants, int cout,
+                       const std::vector<SrcView>& bsrc, int taps, float* out, int k_rows_valid) {
+    memset(&op.p, 0, sizeof op.p);
+    WgradParams& p = op.p;
+    bool all64 = true;
+    int cin_tot = 0;
+    for (const SrcView& v : bsrc) {
+        if (v.C % 32 != 0) return fail("build_wgrad: source channels %d not a multiple of 32", v.C);
+        if (v.C % 64 != 0) all64 = false;
+        cin_tot += v.C;
+    }
+    op.swb = all64 ? 128 : 64;
+    const int CA = op.swb / 2;
+    const int W = avariants[0].W, H = avariants[0].H;
+    const Tile t = choose_tile(W, H, B, 64);
+    p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
+    p.kpix = 64;
+    p.tiles_x = (W + t.TW - 1) / t.TW;
+    p.tiles_y = (H + t.TH - 1) / t.TH;
+    p.tiles_n = (B + t.TN - 1) / t.TN;
+    p.a_variants = (int)avariants.size();
+    p.a_atoms = cout >= 128 ? 2 : 1;
+    p.m_tiles = (cout + 127) / 128;
+    for (size_t i = 0; i < avariants.size(); ++i) {
+        const SrcView& v = avariants[i];
+        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, 64, t.TW, t.TH, t.TN, 128));
+    }
+    for (size_t i = avariants.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    for (size_t i = 0; i < bsrc.size(); ++i) {
+        const SrcView& v = bsrc[i];
+        SDN_OK(encode4(&p.b_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, CA, t.TW, t.TH, t.TN, op.swb));
+    }
+    if (bsrc.size() == 1) p.b_maps[1] = p.b_maps[0];
+    p.taps = taps;
+    p.atoms_per_tap = cin_tot / CA;
+    p.atoms_src0 = bsrc[0].C / CA;
+    const int total_atoms = taps * p.atoms_per_tap;
+    p.G = std::min(total_atoms, 256 / CA);
+    p.n_groups = (total_atoms + p.G - 1) / p.G;
+    p.cout = cout;
+    p.cin_tot = cin_tot;
+    p.k_rows_valid = k_rows_valid;
+    p.out = out;
+    const int stage_bytes = p.a_atoms * p.kpix * 128 + p.G * p.kpix * op.swb;
+    int stages = 8;
+    while (stages > 2 && stages * stage_bytes + 2048 > 200 * 1024) --stages;
+    p.stages = stages;
+    op.smem = stages * stage_bytes + 2048;
+    const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int ctas_per_split = p.n_groups * p.m_tiles * p.a_variants;
+    int split = (2 * c->num_sms + ctas_per_split - 1) / ctas_per_split;
+    split = std::max(1, std::min(split, ptiles));
+    op.grid = dim3(split, p.n_groups, p.m_tiles * p.a_variants);
+    return 0;
+}
+
+// ------------------------------------------------------------------- plan
+static const int kBlockCin[9] = {6, 32, 64, 128, 256, 512, 256, 128, 64};      // enc1..4, bott, dec4..1 (block.0 in)
+static const int kBlockCout[9] = {32, 64, 128, 256, 512, 256, 128, 64, 32};
+static const int kBlockLvl[9] = {1, 2, 3, 4, 5, 4, 3, 2, 1};
+// first parameter index of each block in StereoUNet.parameters() order
+static const int kBlockParam0[9] = {0, 6, 12, 18, 24, 32, 40, 48, 56};
+static const int kUpParam0[4] = {30, 38, 46, 54};  // up4, up3, up2, up1
+
+static void carve(uint8_t*& cur, size_t bytes, void** out) {
+    *out = cur;
+    cur += (bytes + 1023) & ~size_t(1023);
+}
+
+static int plan_and_alloc(sdn_ctx* c) {
+    // Pass 1 computes sizes with cur = nullptr offsets, pass 2 assigns pointers.
+    for (int pass = 0; pass < 2; ++pass) {
+        uint8_t* cur = pass == 0 ? nullptr : c->ws;
+        const int B = c->maxB;
+        auto act = [&](Act& a, int C, int lvl) {
+            a.C = C; a.H = lvl_h(c, lvl); a.W = lvl_w(c, lvl);
+            carve(cur, a.elems(B) * sizeof(bf16), (void**)&a.p);
+        };
+        act(c->x0, 64, 1);
+        size_t wg_off = 0;
+        for (int b = 0; b < 9; ++b) {
+            for (int h = 0; h < 2; ++h) {
+                ConvL& L = c->conv[2 * b + h];
+                L.cin = h == 0 ? kBlockCin[b] : kBlockCout[b];
+                L.cout = kBlockCout[b];
+                L.lvl = kBlockLvl[b];
+                L.first = (b == 0 && h == 0);
+                L.pooled_out = (h == 1 && b < 4);
+                L.p_w = kBlockParam0[b] + 3 * h;
+                L.p_gamma = L.p_w + 1;
+                L.p_beta = L.p_w + 2;
+                L.bn = 2 * b + h;
+                L.has_dgrad = !L.first;
+                act(L.y, L.cout, L.lvl);
+                act(L.a, L.cout, L.lvl);
+                act(L.dy, L.cout, L.lvl);
+                act(L.ga, L.cout, L.lvl);
+                if (L.pooled_out) { act(L.pool, L.cout, L.lvl + 1); act(L.gp, L.cout, L.lvl + 1); }
+                const int kdim = L.first ? 64 : 9 * L.cin;
+                carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wf);
+                carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wd);
+                float* vecs = nullptr;
+                carve(cur, 6 * 512 * sizeof(float), (void**)&vecs);
+                L.scale = vecs; L.shift = vecs + 512; L.mean = vecs + 1024; L.rstd = vecs + 1536;
+                L.c1 = vecs + 2048; L.c2 = vecs + 2560;
+                wg_off += (size_t)kdim * L.cout;
+            }
+        }
+        for (int k = 0; k < 4; ++k) {
+            UpL& U = c->up[k];
+            U.cin = kBlockCout[4 + k];       // 512, 256, 128, 64
+            U.cout = U.cin / 2;
+            U.lvl_in = 5 - k;
+            U.src_layer = 9 + 2 * k;         // bottleneck.3, dec4.3, dec3.3, dec2.3
+            U.p_w = kUpParam0[k];
+            U.p_b = U.p_w + 1;
+            act(U.u, U.cout, U.lvl_in - 1);
+            act(U.gu, U.cout, U.lvl_in - 1);
+            carve(cur, (size_t)4 * U.cin * U.cout * sizeof(bf16), (void**)&U.wf);
+            carve(cur, (size_t)4 * U.cin * U.cout * sizeof(bf16), (void**)&U.wd);
+            carve(cur, (size_t)4 * U.cout * sizeof(float), (void**)&U.bias4);
+            wg_off += (size_t)4 * U.cin * U.cout + U.cout;
+        }
+        // contiguous fp32 weight-gradient workspace (one memset per backward)
+        carve(cur, wg_off * sizeof(float) + 1024, (void**)&c->wg_all);
+        c->wg_all_bytes = wg_off * sizeof(float) + 1024;
+        if (pass == 1) {
+            float* w = c->wg_all;
+            for (int i = 0; i < 18; ++i) {
+                ConvL& L = c->conv[i];
+                L.wg = w;
+                w += (size_t)(L.first ? 64 : 9 * L.cin) * L.cout;
+            }
+            for (int k = 0; k < 4; ++k) {
+                UpL& U = c->up[k];
+                U.wg = w; w += (size_t)4 * U.cin * U.cout;
+                U.bg = w; w += U.cout;
+            }
+        }
+        carve(cur, (size_t)c->num_sms * 2 * 512 * sizeof(float), (void**)&c->stats_partials);
+        carve(cur, (size_t)BWD_BLOCKS * 2 * 512 * sizeof(float), (void**)&c->bwd_partials);
+        carve(cur, 128 * sizeof(float), (void**)&c->head_grads);
+        carve(cur, 64, (void**)&c->n_local);
+        const int parts = ((c->W + 127) / 128) * ((c->H + PRE_ROWS - 1) / PRE_ROWS);
+        carve(cur, (size_t)2 * B * parts * sizeof(float), (void**)&c->gray_part);
+        c->blur_tmp_elems = (size_t)2 * B * 3 * c->H * c->W;
+        carve(cur, c->blur_tmp_elems * sizeof(float), (void**)&c->blur_tmp);
+        if (pass == 0) {
+            c->ws_bytes = (size_t)(cur - (uint8_t*)nullptr) + 4096;
+            CUDA_OK(cudaMalloc((void**)&c->ws, c->ws_bytes));
+            CUDA_OK(cudaMemset(c->ws, 0, c->ws_bytes));
+        }
+    }
+    // wiring of conv inputs
+    for (int b = 0; b < 9; ++b) {
+        ConvL& L0 = c->conv[2 * b];
+        ConvL& L1 = c->conv[2 * b + 1];
+        L1.nsrc = 1; L1.src[0] = &L0.a;
+        if (b == 0) { L0.nsrc = 1; L0.src[0] = &c->x0; }
+        else if (b <= 4) { L0.nsrc = 1; L0.src[0] = &c->conv[2 * b - 1].pool; }
+        else {
+            const int k = b - 5;                    // dec4..dec1 <-> up[k]
+            const int skip = 7 - 2 * k;             // enc4.3, enc3.3, enc2.3, enc1.3
+            L0.nsrc = 2; L0.src[0] = &c->up[k].u; L0.src[1] = &c->conv[skip].a;
+        }
+    }
+    for (int k = 0; k < 4; ++k) c->up[k].src = &c->conv[c->up[k].src_layer].a;
+    return 0;
+}
+
+// (Re)encode every tensor map for batch B.
+static int prepare_batch(sdn_ctx* c, int B) {
+    if (B == c->B) return 0;
+    if (B < 1 || B > c->maxB) return fail("batch %d outside [1, %d]", B, c->maxB);
+    static const SegSpec k3x3[9] = {{0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {0, -1, 0}, {0, 0, 0},
+                                    {0, 1, 0},   {0, -1, 1}, {0, 0, 1},  {0, 1, 1}};
+    for (int i = 0; i < 18; ++i) {
+        ConvL& L = c->conv[i];
+        // ---- forward
+        std::vector<SrcView> av;
+        std::vector<SegSpec> segs;
+        if (L.first) {
+            av.push_back(full_view(c->x0));
+            segs.push_back({0, 0, 0});
+        } else {
+            for (int s = 0; s < L.nsrc; ++s) av.push_back(full_view(*L.src[s]));
+            for (int tap = 0; tap < 9; ++tap)
+                for (int s = 0; s < L.nsrc; ++s) segs.push_back({s, k3x3[tap].dx, k3x3[tap].dy});
+        }
+        SDN_OK(build_gemm(c, L.fprop, B, av, segs, L.wf, L.cout, {full_view(L.y)}, L.cout, nullptr, CG_STATS,
+                          c->stats_partials));
+        // ---- data gradient: conv3x3 of dy with flipped / transposed weights
+        if (L.has_dgrad) {
+            std::vector<SegSpec> dsegs(k3x3, k3x3 + 9);
+            std::vector<SrcView> dv;
+            int n_per = L.cin;
+            if (L.nsrc == 2) {
+                const int k = (i - 10) / 2;
+                const int skip = 7 - 2 * k;
+                dv.push_back(full_view(c->up[k].gu));
+                dv.push_back(full_view(c->conv[skip].ga));
+                n_per = L.cin / 2;
+            } else if (i % 2 == 1) {
+                dv.push_back(full_view(c->conv[i - 1].ga));
+            } else {
+                dv.push_back(full_view(c->conv[i - 1].gp));
+            }
+            SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr));
+        }
+        // ---- weight gradient
+        std::vector<SrcView> bs;
+        if (L.first) bs.push_back(full_view(c->x0));
+        else for (int s = 0; s < L.nsrc; ++s) bs.push_back(full_view(*L.src[s]));
+        SDN_OK(build_wgrad(c, L.wgrad, B, {full_view(L.dy)}, L.cout, bs, L.first ? 1 : 9, L.wg,
+                           L.first ? 64 : 9 * L.cin));
+    }
+    for (int k = 0; k < 4; ++k) {
+        UpL& U = c->up[k];
+        std::vector<SrcView> quads_u, quads_gu;
+        for (int q = 0; q < 4; ++q) { quads_u.push_back(quad_view(U.u, q)); quads_gu.push_back(quad_view(U.gu, q)); }
+        SDN_OK(build_gemm(c, U.fprop, B, {full_view(*U.src)}, {{0, 0, 0}}, U.wf, 4 * U.cout, quads_u, U.cout, U.bias4,
+                          0, nullptr));
+        std::vector<SegSpec> qsegs = {{0, 0, 0}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}};
+        SDN_OK(build_gemm(c, U.dgrad, B, quads_gu, qsegs, U.wd, U.cin, {full_view(c->conv[U.src_layer].ga)}, U.cin,
+                          nullptr, 0, nullptr));
+        SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
+    }
+    c->B = B;
+    return 0;
+}
+
+static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
+    long long need = (work_items + block - 1) / block;
+    long long cap = (long long)c->num_sms * 8;
+    return (int)std::max(1LL, std::min(need, cap));
+}
+
+// bf16 operand cache <- fp32 parameters
+static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
+    for (int i = 0; i < 18; ++i) {
+        ConvL& L = c->conv[i];
+        const float* w = c->params[L.p_w];
+        if (L.first) {
+            pack_weight_kernel<<<ew_grid(c, L.cout * 64, 256), 256, 0, st>>>(w, L.wf, 2, L.cout, L.cin, 64);
+            ++c->launches;
+        } else {
+            const int n = 9 * L.cin * L.cout;
+            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wf, 0, L.cout, L.cin, 0);
+            ++c->launches;
+            if (training) {
+                pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wd, 1, L.cout, L.cin, 0);
+                ++c->launches;
+            }
+        }
+    }
+    for (int k = 0; k < 4; ++k) {
+        UpL& U = c->up[k];
+        const int n = 4 * U.cin * U.cout;
+        pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wf, 3, U.cout, U.cin, 0);
+        ++c->launches;
+        if (training) {
+            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wd, 4, U.cout, U.cin, 0);
+            ++c->launches;
+        }
+        tile_bias_kernel<<<1, 256, 0, st>>>(c->params[U.p_b], U.bias4, U.cout, 4);
+        ++c->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int run_bn_relu(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
+    const int H = L.y.H, W = L.y.W, C = L.cout;
+    if (L.pooled_out) {
+        const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
+        bn_relu_pool_kernel<true><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, L.pool.p, B,
+                                                                         H, W, C);
+    } else {
+        const long long items = (long long)B * H * W * (C / 8);
+        bn_relu_pool_kernel<false><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, nullptr, B,
+                                                                          H, W, C);
+    }
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, int B, int training, int dirty,
+                        cudaStream_t st) {
+    if (!c->have_params) return fail("sdn_forward: call sdn_set_params first");
+    SDN_OK(prepare_batch(c, B));
+    if (dirty) SDN_OK(pack_params(c, training != 0, st));
+    if (!training) {
+        for (int i = 0; i < 18; ++i) {
+            ConvL& L = c->conv[i];
+            bn_prepare_eval_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(L.cout, c->params[L.p_gamma],
+                                                                         c->params[L.p_beta], c->bn_rm[L.bn],
+                                                                         c->bn_rv[L.bn], 1e-5f, L.scale, L.shift);
+            ++c->launches;
+        }
+    }
+    const int H = c->H, W = c->W;
+    im2col_first_kernel<<<ew_grid(c, (long long)B * H * W * 8, 256), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    for (int i = 0; i < 18; ++i) {
+        ConvL& L = c->conv[i];
+        if (i >= 10 && i % 2 == 0) SDN_OK(launch_cg(c, c->up[(i - 10) / 2].fprop, st));
+        GemmOp op = L.fprop;
+        op.p.flags = training ? CG_STATS : 0;
+        SDN_OK(launch_cg(c, op, st));
+        if (training) {
+            const double count = (double)B * L.y.H * L.y.W;
+            bn_finalize_train_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(
+                c->stats_partials, op.grid, L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
+                c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd);
+            ++c->launches;
+        }
+        SDN_OK(run_bn_relu(c, L, B, st));
+    }
+    if (disp != nullptr) {
+        const long long npix = (long long)B * H * W;
+        head_kernel<0><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63],
+                                                              c->params[64], c->params[65], disp, logvar, nullptr,
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr, nullptr, npix);
+        ++c->launches;
+        CUDA_OK(cudaGetLastError());
+    }
+    c->have_forward_train = training != 0;
+    return 0;
+}
+
+// -------------------------------------------------------------- backward
+static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
+    const int H = L.y.H, W = L.y.W, C = L.cout;
+    const double count = (double)B * H * W;
+    const bool pool = L.pooled_out;
+    const long long items = pool ? (long long)B * (H / 2) * (W / 2) * (C / 8) : (long long)B * H * W * (C / 8);
+    int grid = (int)std::max(1LL, std::min((items + 255) / 256, (long long)BWD_BLOCKS));
+    if (pool)
+        bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.scale, L.shift, L.mean, L.rstd,
+                                                         c->bwd_partials, B, H, W, C);
+    else
+        bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, L.scale, L.shift, L.mean, L.rstd,
+                                                          c->bwd_partials, B, H, W, C);
+    ++c->launches;
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(c->bwd_partials, grid, C, count, L.c1, L.c2,
+                                                            c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate);
+    ++c->launches;
+    const int agrid = ew_grid(c, items, 256);
+    if (pool)
+        bn_bwd_apply_kernel<true><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.scale, L.shift, L.mean, L.rstd, L.c1,
+                                                         L.c2, L.dy.p, B, H, W, C);
+    else
+        bn_bwd_apply_kernel<false><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, L.scale, L.shift, L.mean, L.rstd,
+                                                          L.c1, L.c2, L.dy.p, B, H, W, C);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
+    ConvL& L = c->conv[i];
+    SDN_OK(bn_backward(c, L, B, st));
+    SDN_OK(launch_wg(c, L.wgrad, st));
+    if (c->grads[L.p_w] != nullptr) {
+        const int n = 9 * L.cin * L.cout;
+        unpack_grad_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
+                                                               c->accumulate);
+        ++c->launches;
+    }
+    if (L.has_dgrad) SDN_OK(launch_cg(c, L.dgrad, st));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
+    UpL& U = c->up[k];
+    const long long npix = (long long)B * U.gu.H * U.gu.W;
+    dim3 g(U.cout / 8, (unsigned)std::max(1LL, std::min((npix + 255) / 256, (long long)(c->num_sms * 2))));
+    colsum_kernel<<<g, 256, 0, st>>>(U.gu.p, npix, U.cout, U.bg, 0);
+    ++c->launches;
+    SDN_OK(launch_wg(c, U.wgrad, st));
+    if (c->grads[U.p_w] != nullptr) {
+        const int n = 4 * U.cin * U.cout;
+        unpack_grad_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
+        ++c->launches;
+    }
+    if (c->grads[U.p_b] != nullptr) {
+        copy_f32_kernel<<<1, 256, 0, st>>>(U.bg, c->grads[U.p_b], U.cout, c->accumulate);
+        ++c->launches;
+    }
+    SDN_OK(launch_cg(c, U.dgrad, st));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int head_grads_out(sdn_ctx* c, cudaStream_t st) {
+    // head_grads: [0,32) dW_d, [32] db_d, [33,65) dW_l, [65] db_l  -> params 62..65
+    const int off[4] = {0, 32, 33, 65};
+    const int len[4] = {32, 1, 32, 1};
+    for (int j = 0; j < 4; ++j)
+        if (c->grads[62 + j] != nullptr) {
+            copy_f32_kernel<<<1, 32, 0, st>>>(c->head_grads + off[j], c->grads[62 + j], len[j], c->accumulate);
+            ++c->launches;
+        }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int backward_prologue(sdn_ctx* c, int accumulate, cudaStream_t st) {
+    if (!c->have_forward_train) return fail("backward without a training-mode forward");
+    c->accumulate = accumulate;
+    CUDA_OK(cudaMemsetAsync(c->wg_all, 0, c->wg_all_bytes, st));
+    CUDA_OK(cudaMemsetAsync(c->head_grads, 0, 128 * sizeof(float), st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* sdn_last_error(void) { return g_err.c_str(); }
+int sdn_version(void) { return 100; }
+
+int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags) {
+    (void)flags;
+    if (out == nullptr) return fail("sdn_create: out is NULL");
+    if (H % 16 != 0 || W % 16 != 0 || H < 16 || W < 16) return fail("H and W must be positive multiples of 16 (got %dx%d)", H, W);
+    if (max_batch < 1) return fail("max_batch must be >= 1");
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("device %d not available (%d devices)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("sdn requires an sm_100a (B200) device; device %d is sm_%d%d", device, prop.major, prop.minor);
+    SDN_OK(load_encode());
+    SDN_OK(set_smem_attrs());
+    sdn_ctx* c = new sdn_ctx();
+    c->device = device; c->maxB = max_batch; c->H = H; c->W = W;
+    c->num_sms = prop.multiProcessorCount;
+    int r = plan_and_alloc(c);
+    if (r != 0) { if (c->ws) cudaFree(c->ws); delete c; return r; }
+    *out = c;
+    return 0;
+}
+
+int sdn_destroy(sdn_ctx* c) {
+    if (c == nullptr) return 0;
+    cudaSetDevice(c->device);
+    if (c->ws) cudaFree(c->ws);
+    delete c;
+    return 0;
+}
+
+int64_t sdn_workspace_bytes(const sdn_ctx* c) { return c ? (int64_t)c->ws_bytes : 0; }
+int64_t sdn_launch_count(const sdn_ctx* c) { return c ? c->launches : 0; }
+
+int sdn_set_params(sdn_ctx* c, const float* const* params, float* const* grads, float* const* rm, float* const* rv,
+                   int64_t* const* nbt) {
+    if (c == nullptr || params == nullptr) return fail("sdn_set_params: NULL argument");
+    for (int i = 0; i < SDN_NUM_PARAMS; ++i) {
+        if (params[i] == nullptr) return fail("sdn_set_params: param %d is NULL", i);
+        c->params[i] = params[i];
+        c->grads[i] = grads ? grads[i] : nullptr;
+    }
+    for (int i = 0; i < SDN_NUM_BN; ++i) {
+        if (rm == nullptr || rv == nullptr || rm[i] == nullptr || rv[i] == nullptr)
+            return fail("sdn_set_params: BatchNorm buffer %d is NULL", i);
+        c->bn_rm[i] = rm[i];
+        c->bn_rv[i] = rv[i];
+        c->bn_nbt[i] = nbt ? nbt[i] : nullptr;
+    }
+    c->have_params = true;
+    return 0;
+}
+
+int sdn_forward(sdn_ctx* c, const float* x, float* disp, float* logvar, int B, int training, int params_dirty,
+                void* stream) {
+    if (c == nullptr || x == nullptr) return fail("sdn_forward: NULL argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    return forward_impl(c, x, disp, logvar, B, training, params_dirty, (cudaStream_t)stream);
+}
+
+int sdn_backward_begin(sdn_ctx* c, const float* g_disp, const float* g_logvar, int accumulate, void* stream) {
+    if (c == nullptr || g_disp == nullptr) return fail("sdn_backward_begin: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    SDN_OK(backward_prologue(c, accumulate, st));
+    const long long npix = (long long)c->B * c->H * c->W;
+    head_kernel<1><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+                                                          c->params[65], nullptr, nullptr, g_disp, g_logvar, nullptr,
+                                                          nullptr, nullptr, nullptr, nullptr, c->conv[17].ga.p,
+                                                          c->head_grads, npix);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return head_grads_out(c, st);
+}
+
+int sdn_count_valid(sdn_ctx* c, const float* target, const uint8_t* mask, int B, unsigned long long* count_out,
+                    void* stream) {
+    if (c == nullptr || target == nullptr || mask == nullptr || count_out == nullptr)
+        return fail("sdn_count_valid: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(unsigned long long), st));
+    const long long npix = (long long)B * c->H * c->W;
+    mask_count_kernel<<<ew_grid(c, npix, 256), 256, 0, st>>>(target, mask, npix, count_out);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* disp, float* logvar, float* sums4,
+                   unsigned long long* count, const unsigned long long* n_norm_dev, int with_backward, int accumulate,
+                   void* stream) {
+    if (c == nullptr || target == nullptr || mask == nullptr || sums4 == nullptr || count == nullptr)
+        return fail("sdn_loss_begin: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (c->B < 1) return fail("sdn_loss_begin: no forward has run");
+    const long long npix = (long long)c->B * c->H * c->W;
+    if (with_backward) {
+        SDN_OK(backward_prologue(c, accumulate, st));
+        if (n_norm_dev == nullptr) {
+            SDN_OK(sdn_count_valid(c, target, mask, c->B, c->n_local, stream));
+            n_norm_dev = c->n_local;
+        }
+    } else {
+        CUDA_OK(cudaMemsetAsync(c->head_grads, 0, 128 * sizeof(float), st));
+        CUDA_OK(cudaMemsetAsync(c->n_local, 0, sizeof(unsigned long long), st));
+        n_norm_dev = c->n_local;  // zero -> gradients are zero and unused
+    }
+    // the gradient buffer of dec1's output doubles as scratch on the metrics-only path
+    head_kernel<2><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+                                                          c->params[65], disp, logvar, nullptr, nullptr, target, mask,
+                                                          n_norm_dev, sums4, count, c->conv[17].ga.p, c->head_grads,
+                                                          npix);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    if (with_backward) return head_grads_out(c, st);
+    return 0;
+}
+
+int sdn_stage_param_range(int stage, int* first, int* num) {
+    static const int f[SDN_NUM_STAGES] = {38, 30, 24, 0};
+    static const int n[SDN_NUM_STAGES] = {28, 8, 6, 24};
+    if (stage < 0 || stage >= SDN_NUM_STAGES || first == nullptr || num == nullptr)
+        return fail("sdn_stage_param_range: bad stage %d", stage);
+    *first = f[stage];
+    *num = n[stage];
+    return 0;
+}
+
+int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
+    if (c == nullptr) return fail("sdn_backward_stage: NULL ctx");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->have_forward_train) return fail("backward without a training-mode forward");
+    const int B = c->B;
+    switch (stage) {
+        case 0:  // dec1, up1, dec2, up2, dec3, up3 (+ heads, done in *_begin)
+            SDN_OK(conv_backward(c, 17, B, st)); SDN_OK(conv_backward(c, 16, B, st)); SDN_OK(up_backward(c, 3, B, st));
+            SDN_OK(conv_backward(c, 15, B, st)); SDN_OK(conv_backward(c, 14, B, st)); SDN_OK(up_backward(c, 2, B, st));
+            SDN_OK(conv_backward(c, 13, B, st)); SDN_OK(conv_backward(c, 12, B, st)); SDN_OK(up_backward(c, 1, B, st));
+            break;
+        case 1:  // dec4, up4
+            SDN_OK(conv_backward(c, 11, B, st)); SDN_OK(conv_backward(c, 10, B, st)); SDN_OK(up_backward(c, 0, B, st));
+            break;
+        case 2:  // bottleneck
+            SDN_OK(conv_backward(c, 9, B, st)); SDN_OK(conv_backward(c, 8, B, st));
+            break;
+        case 3:  // enc4 .. enc1
+            for (int i = 7; i >= 0; --i) SDN_OK(conv_backward(c, i, B, st));
+            break;
+        default:
+            return fail("sdn_backward_stage: bad stage %d", stage);
+    }
+    return 0;
+}
+
+int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
+                   int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
+                   unsigned long long* valid_count, void* stream) {
+    if (c == nullptr || left == nullptr || right == nullptr || disparity == nullptr || input == nullptr ||
+        target == nullptr || mask == nullptr)
+        return fail("sdn_preprocess: NULL argument");
+    if (B < 1 || B > c->maxB) return fail("sdn_preprocess: batch %d outside [1, %d]", B, c->maxB);
+    if (Hs < 1 || Ws < 1) return fail("sdn_preprocess: bad source size %dx%d", Hs, Ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    const int H = c->H, W = c->W;
+    const int xblocks = (W + 127) / 128, yblocks = (H + PRE_ROWS - 1) / PRE_ROWS;
+    const int parts = xblocks * yblocks;
+    if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
+    const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
+    decode_resize_kernel<<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input, target, mask,
+                                                         valid_count, aug, aug ? c->gray_part : nullptr, parts);
+    ++c->launches;
+    if (aug != nullptr) {
+        augment_point_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(input, B, H, W, aug, c->gray_part, parts,
+                                                                              c->blur_tmp);
+        ++c->launches;
+        blur_noise_kernel<5><<<dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st>>>(input, B, H, W, aug,
+                                                                                              c->blur_tmp);
+        ++c->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdn_debug_read(sdn_ctx* c, int which, int kind, float* host_out, int64_t capacity, int* dims4) {
+    if (c == nullptr || host_out == nullptr || dims4 == nullptr) return fail("sdn_debug_read: NULL argument");
+    const Act* a = nullptr;
+    if (which >= 0 && which < 18) {
+        ConvL& L = c->conv[which];
+        a = kind == 0 ? &L.y : kind == 1 ? &L.a : kind == 2 ? &L.dy : kind == 3 ? &L.ga : nullptr;
+    } else if (which >= 100 && which < 104) {
+        UpL& U = c->up[which - 100];
+        a = kind == 0 ? &U.u : kind == 3 ? &U.gu : nullptr;
+    } else if (which == 200) {
+        a = &c->x0;
+    }
+    if (a == nullptr || a->p == nullptr) return fail("sdn_debug_read: bad selector %d/%d", which, kind);
+    const size_t n = a->elems(c->B);
+    dims4[0] = c->B; dims4[1] = a->H; dims4[2] = a->W; dims4[3] = a->C;
+    if ((int64_t)n > capacity) return fail("sdn_debug_read: capacity %lld < %zu", (long long)capacity, n);
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    std::vector<uint16_t> tmp(n);
+    CUDA_OK(cudaMemcpy(tmp.data(), a->p, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t u = (uint32_t)tmp[i] << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        host_out[i] = f;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Device input pipeline: the per-sample work the reference does on CPU DataLoader
+// workers (src/foundation_stereo_depth/dataset.py), as memory-bound kernels.
+//
+//   decode_resize_kernel : dataset.py:23-30 (depth_uint8_decoding), :184-193
+//                          (_load_rgb: /255 + bilinear, align_corners=False, no
+//                          antialias), :195-212 (_load_disparity: decode -> bilinear ->
+//                          * W_out/W_in), :305-311 (cat([L,R]), valid_mask = target > 0).
+//                          Bit-exact against the CPU path: every multiply / add that
+//                          the CPU kernel performs is spelled with an explicit
+//                          round-to-nearest intrinsic so nvcc cannot re-contract it.
+//   augment_point_kernel : dataset.py:248-270 (_augment_rgb) brightness -> contrast ->
+//                          saturation -> hue -> gamma [-> noise -> clamp], semantics of
+//                          torchvision/transforms/_functional_tensor.py.
+//   blur_noise_kernel    : the 5x5 Gaussian blur (reflect padding) for the few views
+//                          whose blur coin came up, then noise + clamp.
+// Raw uint8 HWC images are the kernel input: PNG inflate is out of scope.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdn {
+
+// Per-view photometric parameters (explicit, so the reference's samplers
+// dataset.py:214-246 can be replayed exactly by tests).
+struct AugParams {
+    float brightness;  // f_b
+    float contrast;    // f_c
+    float saturation;  // f_s
+    float hue;         // delta h in [-0.5, 0.5]
+    float gamma;       // gamma
+    float blur_sigma;  // > 0 => blur with this sigma
+    float noise_std;   // > 0 => add N(0,1)*noise_std
+    uint32_t noise_seed;
+};
+
+// PyTorch area_pixel_compute_source_index + guard_index_and_lambda
+// (aten/src/ATen/native/UpSample.h), align_corners = false, in fp32.
+__device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, int out_size, int& i0, int& i1,
+                                             float& l0, float& l1) {
+    if (in_size == out_size) { i0 = dst; i1 = dst; l0 = 1.f; l1 = 0.f; return; }
+    float real = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    if (real < 0.f) real = 0.f;
+    int idx = (int)floorf(real);
+    if (idx > in_size - 1) idx = in_size - 1;
+    float lam = __fsub_rn(real, (float)idx);
+    lam = fminf(fmaxf(lam, 0.f), 1.f);
+    i0 = idx;
+    i1 = idx + (idx < in_size - 1 ? 1 : 0);
+    l1 = lam;
+    l0 = __fsub_rn(1.f, lam);
+}
+
+// out = h0*(w0*a + w1*b) + h1*(w0*c + w1*e) in the association/contraction the
+// CPU kernel uses (second product rounded, then fused with the first).
+__device__ __forceinline__ float bilerp(float a, float b, float c, float e, float w0, float w1, float h0, float h1) {
+    const float top = __fmaf_rn(w0, a, __fmul_rn(w1, b));
+    const float bot = __fmaf_rn(w0, c, __fmul_rn(w1, e));
+    return __fmaf_rn(h0, top, __fmul_rn(h1, bot));
+}
+
+__device__ __forceinline__ float gray_of(float r, float g, float b) {
+    // (0.2989 * r + 0.587 * g + 0.114 * b) evaluated left to right in fp32
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+__device__ __forceinline__ float blend(float x, float y, float ratio, float one_minus) {
+    // _blend: (ratio * img1 + (1 - ratio) * img2).clamp(0, 1)
+    return fminf(fmaxf(__fadd_rn(__fmul_rn(ratio, x), __fmul_rn(one_minus, y)), 0.f), 1.f);
+}
+
+// grid = (ceil(W/128) * ceil(H/ROWS_PER_BLOCK), B); block = 128 threads (one output column each).
+constexpr int PRE_ROWS = 8;
+
+__global__ void __launch_bounds__(128) decode_resize_kernel(
+    const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, const uint8_t* __restrict__ D, int B, int Hs, int Ws,
+    int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
+    unsigned long long* __restrict__ valid_count, const AugParams* __restrict__ aug, float* __restrict__ gray_part,
+    int parts_per_view) {
+    const int n = blockIdx.y;
+    const int xblocks = (W + 127) / 128;
+    const int xb = blockIdx.x % xblocks;
+    const int yb = blockIdx.x / xblocks;
+    const int x = xb * 128 + threadIdx.x;
+    const float sy = (float)Hs / (float)H;
+    const float sx = (float)Ws / (float)W;
+    const float wscale = (float)((double)W / (double)Ws);
+    const size_t src_img = (size_t)Hs * Ws * 3;
+    const uint8_t* Ln = L + (size_t)n * src_img;
+    const uint8_t* Rn = R + (size_t)n * src_img;
+    const uint8_t* Dn = D + (size_t)n * src_img;
+    const size_t plane = (size_t)H * W;
+    float gsumL = 0.f, gsumR = 0.f;
+    unsigned int cnt = 0;
+    float fbL = 1.f, fbR = 1.f;
+    if (aug != nullptr) { fbL = aug[2 * n].brightness; fbR = aug[2 * n + 1].brightness; }
+    if (x < W) {
+        int x0, x1;
+        float w0, w1;
+        bilinear_src(sx, x, Ws, W, x0, x1, w0, w1);
+        for (int yy = 0; yy < PRE_ROWS; ++yy) {
+            const int y = yb * PRE_ROWS + yy;
+            if (y >= H) break;
+            int y0, y1;
+            float h0, h1;
+            bilinear_src(sy, y, Hs, H, y0, y1, h0, h1);
+            const size_t o00 = ((size_t)y0 * Ws + x0) * 3, o01 = ((size_t)y0 * Ws + x1) * 3;
+            const size_t o10 = ((size_t)y1 * Ws + x0) * 3, o11 = ((size_t)y1 * Ws + x1) * 3;
+            const size_t opix = (size_t)y * W + x;
+            float rgbL[3], rgbR[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float a = __fdiv_rn((float)__ldg(Ln + o00 + c), 255.f);
+                const float b = __fdiv_rn((float)__ldg(Ln + o01 + c), 255.f);
+                const float cc = __fdiv_rn((float)__ldg(Ln + o10 + c), 255.f);
+                const float e = __fdiv_rn((float)__ldg(Ln + o11 + c), 255.f);
+                rgbL[c] = bilerp(a, b, cc, e, w0, w1, h0, h1);
+                input[((size_t)n * 6 + c) * plane + opix] = rgbL[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float a = __fdiv_rn((float)__ldg(Rn + o00 + c), 255.f);
+                const float b = __fdiv_rn((float)__ldg(Rn + o01 + c), 255.f);
+                const float cc = __fdiv_rn((float)__ldg(Rn + o10 + c), 255.f);
+                const float e = __fdiv_rn((float)__ldg(Rn + o11 + c), 255.f);
+                rgbR[c] = bilerp(a, b, cc, e, w0, w1, h0, h1);
+                input[((size_t)n * 6 + 3 + c) * plane + opix] = rgbR[c];
+            }
+            float dv[4];
+            const size_t offs[4] = {o00, o01, o10, o11};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float r = (float)__ldg(Dn + offs[k]), g = (float)__ldg(Dn + offs[k] + 1),
+                            b = (float)__ldg(Dn + offs[k] + 2);
+                // exact in fp32 (max 16,646,655 < 2^24): R*255*255 + G*255 + B, then one rounded divide
+                const float s = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(r, 255.f), 255.f), __fmul_rn(g, 255.f)), b);
+                dv[k] = __fdiv_rn(s, 1000.f);
+            }
+            const float t = __fmul_rn(bilerp(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
+            target[(size_t)n * plane + opix] = t;
+            const bool valid = t > 0.f;
+            mask[(size_t)n * plane + opix] = valid ? 1 : 0;
+            cnt += (valid && isfinite(t)) ? 1u : 0u;
+            if (aug != nullptr) {
+                // brightness-adjusted grayscale, whose image mean adjust_contrast needs
+                gsumL += gray_of(blend(rgbL[0], 0.f, fbL, 1.f - fbL), blend(rgbL[1], 0.f, fbL, 1.f - fbL),
+                                 blend(rgbL[2], 0.f, fbL, 1.f - fbL));
+                gsumR += gray_of(blend(rgbR[0], 0.f, fbR, 1.f - fbR), blend(rgbR[1], 0.f, fbR, 1.f - fbR),
+                                 blend(rgbR[2], 0.f, fbR, 1.f - fbR));
+            }
+        }
+    }
+    // block reduction (4 warps)
+    __shared__ float redL[4], redR[4];
+    __shared__ unsigned int redC[4];
+    for (int o = 16; o > 0; o >>= 1) {
+        gsumL += __shfl_xor_sync(0xffffffffu, gsumL, o);
+        gsumR += __shfl_xor_sync(0xffffffffu, gsumR, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { redL[threadIdx.x >> 5] = gsumL; redR[threadIdx.x >> 5] = gsumR; redC[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (gray_part != nullptr) {
+            gray_part[(size_t)(2 * n) * parts_per_view + blockIdx.x] = (redL[0] + redL[1]) + (redL[2] + redL[3]);
+            gray_part[(size_t)(2 * n + 1) * parts_per_view + blockIdx.x] = (redR[0] + redR[1]) + (redR[2] + redR[3]);
+        }
+        if (valid_count != nullptr) {
+            const unsigned int c = redC[0] + redC[1] + redC[2] + redC[3];
+            if (c) atomicAdd(valid_count, (unsigned long long)c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- Philox RNG
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// three standard normals for (view, pixel)
+__device__ __forceinline__ void normal3(uint32_t seed, uint32_t view, uint32_t pix, float (&z)[3]) {
+    uint32_t r[4];
+    philox4x32_10(pix, view, 0x5DEECE66u, 0u, seed, 0xB5297A4Du, r);
+    const float u0 = ((float)(r[0] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u1 = ((float)(r[1] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u2 = ((float)(r[2] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u3 = ((float)(r[3] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+    float s, c;
+    sincospif(2.f * u1, &s, &c);
+    z[0] = ra * c;
+    z[1] = ra * s;
+    z[2] = rb * cospif(2.f * u3);
+}
+
+// brightness .. gamma for one pixel, torchvision tensor semantics
+__device__ __forceinline__ void augment_pixel(float (&v)[3], const AugParams& a, float gray_mean) {
+    const float fb = a.brightness, fc = a.contrast, fs = a.saturation;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = blend(v[c], 0.f, fb, 1.f - fb);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = blend(v[c], gray_mean, fc, 1.f - fc);
+    const float g = gray_of(v[0], v[1], v[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = blend(v[c], g, fs, 1.f - fs);
+    // adjust_hue: _rgb2hsv -> (h + delta) mod 1 -> _hsv2rgb
+    const float r = v[0], gg = v[1], b = v[2];
+    const float maxc = fmaxf(r, fmaxf(gg, b)), minc = fminf(r, fminf(gg, b));
+    const bool eqc = maxc == minc;
+    const float cr = maxc - minc;
+    const float s = __fdiv_rn(cr, eqc ? 1.f : maxc);
+    const float div = eqc ? 1.f : cr;
+    const float rc = __fdiv_rn(maxc - r, div), gc = __fdiv_rn(maxc - gg, div), bc = __fdiv_rn(maxc - b, div);
+    const float hr = (maxc == r) ? (bc - gc) : 0.f;
+    const float hg = ((maxc == gg) && (maxc != r)) ? __fadd_rn(2.f, rc) - bc : 0.f;
+    const float hb = ((maxc != gg) && (maxc != r)) ? __fadd_rn(4.f, gc) - rc : 0.f;
+    float h = __fadd_rn(__fadd_rn(hr, hg), hb);
+    h = fmodf(__fadd_rn(__fdiv_rn(h, 6.f), 1.f), 1.f);
+    h = __fadd_rn(h, a.hue);
+    h = h - floorf(h);  // python-style remainder by 1.0
+    if (h >= 1.f) h = 0.f;
+    const float h6 = __fmul_rn(h, 6.f);
+    const float fi = floorf(h6);
+    const float f = __fsub_rn(h6, fi);
+    int i = ((int)fi) % 6;
+    if (i < 0) i += 6;
+    const float p = fminf(fmaxf(__fmul_rn(maxc, __fsub_rn(1.f, s)), 0.f), 1.f);
+    const float q = fminf(fmaxf(__fmul_rn(maxc, __fsub_rn(1.f, __fmul_rn(s, f))), 0.f), 1.f);
+    const float t = fminf(fmaxf(__fmul_rn(maxc, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, f)))), 0.f), 1.f);
+    const float vv = maxc;
+    float ro, go, bo;
+    switch (i) {
+        case 0: ro = vv; go = t; bo = p; break;
+        case 1: ro = q; go = vv; bo = p; break;
+        case 2: ro = p; go = vv; bo = t; break;
+        case 3: ro = p; go = q; bo = vv; break;
+        case 4: ro = t; go = p; bo = vv; break;
+        default: ro = vv; go = p; bo = q; break;
+    }
+    // adjust_gamma: (1.0 * x ** gamma).clamp(0, 1)
+    v[0] = fminf(fmaxf(powf(ro, a.gamma), 0.f), 1.f);
+    v[1] = fminf(fmaxf(powf(go, a.gamma), 0.f), 1.f);
+    v[2] = fminf(fmaxf(powf(bo, a.gamma), 0.f), 1.f);
+}
+
+// grid = (ceil(H*W/256), 2*B); in place on input[B,6,H,W]; blurred views are
+// written (post-gamma) to blur_tmp[view] instead and finished by blur_noise_kernel.
+__global__ void __launch_bounds__(256) augment_point_kernel(float* __restrict__ input, int B, int H, int W,
+                                                            const AugParams* __restrict__ aug,
+                                                            const float* __restrict__ gray_part, int parts_per_view,
+                                                            float* __restrict__ blur_tmp) {
+    const int view = blockIdx.y;  // 2*n + {0: left, 1: right}
+    const AugParams a = aug[view];
+    __shared__ float s_mean;
+    if (threadIdx.x == 0) {
+        // fixed-order fp64 sum of the per-block partials: deterministic
+        double s = 0.0;
+        for (int i = 0; i < parts_per_view; ++i) s += (double)gray_part[(size_t)view * parts_per_view + i];
+        s_mean = (float)(s / ((double)H * (double)W));
+    }
+    __syncthreads();
+    const size_t plane = (size_t)H * W;
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= plane) return;
+    float* base = input + ((size_t)(view >> 1) * 6 + (view & 1) * 3) * plane;
+    float v[3] = {base[pix], base[plane + pix], base[2 * plane + pix]};
+    augment_pixel(v, a, s_mean);
+    if (a.blur_sigma > 0.f) {
+        float* t = blur_tmp + (size_t)view * 3 * plane;
+        t[pix] = v[0]; t[plane + pix] = v[1]; t[2 * plane + pix] = v[2];
+        return;
+    }
+    if (a.noise_std > 0.f) {
+        float z[3];
+        normal3(a.noise_seed, (uint32_t)view, (uint32_t)pix, z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = fmaf(z[c], a.noise_std, v[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) base[c * plane + pix] = fminf(fmaxf(v[c], 0.f), 1.f);
+}
+
+// 5x5 Gaussian (outer product of the normalised 1-D kernel, reflect padding,
+// torchvision gaussian_blur) + noise + clamp, only for views with blur_sigma > 0.
+// grid = (ceil(W/32), ceil(H/8), 2*B), block = (32, 8).
+template <int KS>
+__global__ void __launch_bounds__(256) blur_noise_kernel(float* __restrict__ input, int B, int H, int W,
+                                                         const AugParams* __restrict__ aug,
+                                                         const float* __restrict__ blur_tmp) {
+    const int view = blockIdx.z;
+    const AugParams a = aug[view];
+    if (!(a.blur_sigma > 0.f)) return;
+    constexpr int R = KS / 2;
+    __shared__ float tile[3][8 + 2 * R][32 + 2 * R];
+    __shared__ float k1d[KS];
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        float pdf[KS], sum = 0.f;
+        for (int i = 0; i < KS; ++i) {
+            const float xv = -0.5f * (KS - 1) + (float)i;
+            const float q = __fdiv_rn(xv, a.blur_sigma);
+            pdf[i] = expf(__fmul_rn(-0.5f, __fmul_rn(q, q)));
+            sum = __fadd_rn(sum, pdf[i]);
+        }
+        for (int i = 0; i < KS; ++i) k1d[i] = __fdiv_rn(pdf[i], sum);
+    }
+    const size_t plane = (size_t)H * W;
+    const float* src = blur_tmp + (size_t)view * 3 * plane;
+    const int x0 = blockIdx.x * 32 - R, y0 = blockIdx.y * 8 - R;
+    for (int idx = threadIdx.y * 32 + threadIdx.x; idx < 3 * (8 + 2 * R) * (32 + 2 * R); idx += 256) {
+        const int c = idx / ((8 + 2 * R) * (32 + 2 * R));
+        const int rem = idx % ((8 + 2 * R) * (32 + 2 * R));
+        const int ty = rem / (32 + 2 * R), tx = rem % (32 + 2 * R);
+        int yy = y0 + ty, xx = x0 + tx;
+        // reflect (no edge repeat): -1 -> 1, H -> H-2
+        if (yy < 0) yy = -yy;
+        if (yy >= H) yy = 2 * H - 2 - yy;
+        if (xx < 0) xx = -xx;
+        if (xx >= W) xx = 2 * W - 2 - xx;
+        yy = min(max(yy, 0), H - 1);
+        xx = min(max(xx, 0), W - 1);
+        tile[c][ty][tx] = src[c * plane + (size_t)yy * W + xx];
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t pix = (size_t)y * W + x;
+    float z[3] = {0.f, 0.f, 0.f};
+    if (a.noise_std > 0.f) normal3(a.noise_seed, (uint32_t)view, (uint32_t)pix, z);
+    float* base = input + ((size_t)(view >> 1) * 6 + (view & 1) * 3) * plane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < KS; ++i)
+#pragma unroll
+            for (int j = 0; j < KS; ++j)
+                acc = fmaf(__fmul_rn(k1d[i], k1d[j]), tile[c][threadIdx.y + i][threadIdx.x + j], acc);
+        if (a.noise_std > 0.f) acc = fmaf(z[c], a.noise_std, acc);
+        base[c * plane + pix] = fminf(fmaxf(acc, 0.f), 1.f);
+    }
+}
+
+}  // namespace sdn

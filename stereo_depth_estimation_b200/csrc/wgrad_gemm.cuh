@@ -1,0 +1,187 @@
+// Weight-gradient GEMM on tcgen05 tensor cores (sm_100a).
+//
+// dW[k = (tap, ci)][co] = sum over pixels p of dY[p][co] * X[p + tap][ci]
+// (the weight gradient of nn.Conv2d / nn.ConvTranspose2d in the reference model,
+// src/foundation_stereo_depth/model.py:36,39,67-73, which the reference gets from
+// autograd at train.py:342).
+//
+// The contraction index is the PIXEL, which is the slow dimension of our NHWC
+// tensors, so both operands are "MN-major" for tcgen05.mma: a TMA box
+// (64 channels, TW, TH, TN) lands in shared memory as [pixels][128 B] with the
+// 128-byte swizzle, which is exactly the canonical MN-major SW128 atom column
+// (8-row groups 1024 B apart = SBO, channel atoms LBO apart).
+//   A (M side) = dY: one or two 64-channel atoms -> M = 128 (with one atom the
+//                second half aliases the first via LBO = 0 and is ignored).
+//   B (N side) = up to G atoms, each its own TMA box: a (filter tap, channel
+//                block) of X shifted by the tap; N = atoms * CA <= 256.
+// Each CTA owns one (co tile, atom group) and a split of the pixel tiles; fp32
+// partial sums are merged with red.global.add into a [k][co] workspace.
+#pragma once
+#include "ptx.cuh"
+
+namespace sdn {
+
+struct alignas(64) WgradParams {
+    CUtensorMap a_maps[4];  // dY variants (convT: the 4 output quadrants)
+    CUtensorMap b_maps[2];  // X sources (skip-concat: two tensors)
+    int a_atoms;            // 1 or 2 64-channel atoms on the M side
+    int a_variants;         // 1, or 4 for ConvTranspose2d
+    int m_tiles;            // ceil(Cout / 128)
+    int G;                  // B atoms per CTA
+    int taps;               // 9 (3x3) or 1
+    int atoms_per_tap;      // Cin_total / CA
+    int atoms_src0;         // atoms that come from b_maps[0]
+    int n_groups;           // ceil(taps * atoms_per_tap / G)
+    int tiles_x, tiles_y, tiles_n, TW, TH, TN;
+    int kpix;               // TW*TH*TN (64 or 128)
+    int stages;
+    int cout;               // valid output channels (row length of the workspace)
+    int cin_tot;
+    int k_rows_valid;       // rows of the workspace that exist
+    float* out;             // [a_variants][taps * cin_tot][cout] fp32, pre-zeroed
+};
+
+template <int SWB>
+__global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+    constexpr int CA = SWB / 2;  // channels per B atom
+    constexpr uint32_t LAYOUT_B = (SWB == 128) ? 2u : 4u;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    const int a_tile_bytes = p.kpix * 128;
+    const int b_tile_bytes = p.kpix * SWB;
+    const int stage_bytes = p.a_atoms * a_tile_bytes + p.G * b_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* tfull_bar = bars + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int variant = blockIdx.z / p.m_tiles;
+    const int m_tile = blockIdx.z % p.m_tiles;
+    const int group = blockIdx.y;
+    const int total_atoms = p.taps * p.atoms_per_tap;
+    const int atom0 = group * p.G;
+    const int natoms = min(p.G, total_atoms - atom0);
+    const int N = natoms * CA;
+    const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr_smem, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < ptiles; t += gridDim.x) ++my_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::prefetch_tmap(&p.a_maps[variant]);
+            ptx::prefetch_tmap(&p.b_maps[0]);
+            ptx::prefetch_tmap(&p.b_maps[1]);
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx_bytes = p.a_atoms * a_tile_bytes + natoms * b_tile_bytes;
+            for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
+                const int tx = t % p.tiles_x;
+                const int ty = (t / p.tiles_x) % p.tiles_y;
+                const int tn = t / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * stage_bytes;
+                uint8_t* b_dst = a_dst + p.a_atoms * a_tile_bytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                for (int i = 0; i < p.a_atoms; ++i)
+                    ptx::tma_load_4d(a_dst + i * a_tile_bytes, &p.a_maps[variant], &full_bar[s],
+                                     m_tile * 128 + i * 64, x0, y0, n0);
+                for (int g = 0; g < natoms; ++g) {
+                    const int u = atom0 + g;
+                    const int tap = u / p.atoms_per_tap;
+                    const int ca = u % p.atoms_per_tap;
+                    int dx = 0, dy = 0;
+                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                    const int src = ca < p.atoms_src0 ? 0 : 1;
+                    const int c0 = (src == 0 ? ca : ca - p.atoms_src0) * CA;
+                    ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[src], &full_bar[s], c0, x0 + dx, y0 + dy, n0);
+                }
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t idesc = ptx::make_idesc_bf16(128, N, 1, 1);
+            const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
+            for (int it = 0; it < my_tiles; ++it) {
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + p.a_atoms * a_tile_bytes;
+                for (int k = 0; k < p.kpix / 16; ++k) {
+                    // 16 pixels = two 8-row groups: advance by 16 rows of the atom column
+                    const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 16 * 128, a_lbo, 1024, 2u);
+                    const uint64_t bdesc =
+                        ptx::make_smem_desc(b_addr + k * 16 * SWB, uint32_t(b_tile_bytes), 8 * SWB, LAYOUT_B);
+                    ptx::tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                ptx::tc_commit(&empty_bar[s]);
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+            ptx::tc_commit(tfull_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int co = m_tile * 128 + r;
+        const bool row_ok = (r < p.a_atoms * 64) && (co < p.cout);
+        if (my_tiles > 0) {
+            ptx::mbar_wait(tfull_bar, 0);
+            ptx::tc_fence_after();
+            float* out = p.out + size_t(variant) * p.taps * p.cin_tot * p.cout;
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+            for (int ch = 0; ch < N / 32; ++ch) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + ch * 32, v);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    const int cn0 = ch * 32;
+                    const int g = cn0 / CA;
+                    const int u = atom0 + g;
+                    const int tap = u / p.atoms_per_tap;
+                    const int ca = u % p.atoms_per_tap;
+                    const int krow0 = tap * p.cin_tot + ca * CA + (cn0 % CA);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int krow = krow0 + j;
+                        if (krow < p.k_rows_valid) atomicAdd(out + size_t(krow) * p.cout + co, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace sdn
