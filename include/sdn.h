@@ -99,10 +99,15 @@ int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask
  * Outputs: input fp32 [B,6,H,W], target fp32 [B,1,H,W], mask u8 [B,1,H,W],
  * *valid_count (device u64, optional) = sum(mask & isfinite(target)).
  * aug: 2*B parameter structs on the DEVICE (left, right per sample) or NULL for
- * augment=False. */
+ * augment=False.
+ * flags: SDN_RESIZE_FOURTERM selects the other of the two fused-multiply-add
+ * orderings that torch's CPU bilinear kernel is compiled with (it is the one a
+ * single-threaded DataLoader worker runs on small / 3-channel images; results
+ * differ by <= 1 ulp, indices and weights are identical); 0 = canonical form. */
+#define SDN_RESIZE_FOURTERM 1u
 int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
-                   unsigned long long* valid_count, void* stream);
+                   unsigned long long* valid_count, unsigned flags, void* stream);
 
 /* Test / debug access to the NHWC bf16 activations of the last forward:
  * which = conv layer index 0..17; kind 0 = pre-BN conv output, 1 = post

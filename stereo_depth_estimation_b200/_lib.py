@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 NUM_PARAMS = 66
 NUM_BN = 18
 NUM_STAGES = 4
+RESIZE_FOURTERM = 1
 
 # every symbol include/sdn.h declares (tests check that the .so exports them all)
 EXPORTS = (
@@ -94,7 +95,7 @@ def load() -> ctypes.CDLL:
     lib.sdn_count_valid.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p]
+                                   c_void_p, c_void_p, c_void_p, c_uint, c_void_p]
     lib.sdn_debug_read.restype = c_int
     lib.sdn_debug_read.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), c_int64, POINTER(c_int)]
     _lib = lib

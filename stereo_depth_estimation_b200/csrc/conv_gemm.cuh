@@ -48,6 +48,7 @@ struct alignas(64) ConvGemmParams {
     int kblocks_total;
     int tiles_x, tiles_y, tiles_n;  // M tiling of (W, H, batch)
     int TW, TH, TN;                 // pixel box, TW*TH*TN == 128
+    int img_w, img_h, img_n;        // output extent (rows of a ragged box outside it are zeroed)
     int n_tiles;                    // N tiling
     int n_tiles_per_dmap;           // N tiles that land in one D map
     int n_total;                    // n_tiles * BLOCK_N
@@ -212,6 +213,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             const int tn = m_tile / (p.tiles_x * p.tiles_y);
             const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
 
+            // A box row outside the image still sees in-image neighbours through the
+            // shifted taps, so its accumulator is not zero: zero it (the TMA store
+            // clips it anyway, but the BatchNorm statistics must not see it).
+            const bool row_in_image = (x0 + r % p.TW < p.img_w) && (y0 + (r / p.TW) % p.TH < p.img_h) &&
+                                      (n0 + r / (p.TW * p.TH) < p.img_n);
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BLOCK_N;
@@ -231,6 +237,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                 if (do_relu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (!row_in_image) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
                 }
                 const int cbk = (ch * 32) / Cfg::DCH;
                 const int j0 = ((ch * 32) % Cfg::DCH) / 8;

@@ -314,6 +314,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.tiles_x = (W + t.TW - 1) / t.TW;
     p.tiles_y = (H + t.TH - 1) / t.TH;
     p.tiles_n = (B + t.TN - 1) / t.TN;
+    p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
         SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, t.TW, t.TH, t.TN, op.swa));
@@ -941,7 +942,7 @@ int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
 
 int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
-                   unsigned long long* valid_count, void* stream) {
+                   unsigned long long* valid_count, unsigned flags, void* stream) {
     if (c == nullptr || left == nullptr || right == nullptr || disparity == nullptr || input == nullptr ||
         target == nullptr || mask == nullptr)
         return fail("sdn_preprocess: NULL argument");
@@ -954,8 +955,14 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     const int parts = xblocks * yblocks;
     if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
     const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
-    decode_resize_kernel<<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input, target, mask,
-                                                         valid_count, aug, aug ? c->gray_part : nullptr, parts);
+    if (flags & SDN_RESIZE_FOURTERM)
+        decode_resize_kernel<true><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
+                                                                   target, mask, valid_count, aug,
+                                                                   aug ? c->gray_part : nullptr, parts);
+    else
+        decode_resize_kernel<false><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
+                                                                    target, mask, valid_count, aug,
+                                                                    aug ? c->gray_part : nullptr, parts);
     ++c->launches;
     if (aug != nullptr) {
         augment_point_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(input, B, H, W, aug, c->gray_part, parts,

@@ -38,7 +38,8 @@ struct AugParams {
 __device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, int out_size, int& i0, int& i1,
                                              float& l0, float& l1) {
     if (in_size == out_size) { i0 = dst; i1 = dst; l0 = 1.f; l1 = 0.f; return; }
-    float real = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    // torch's CPU build contracts scale * (dst + 0.5) - 0.5 into one fused multiply-add
+    float real = __fmaf_rn(scale, __fadd_rn((float)dst, 0.5f), -0.5f);
     if (real < 0.f) real = 0.f;
     int idx = (int)floorf(real);
     if (idx > in_size - 1) idx = in_size - 1;
@@ -50,9 +51,17 @@ __device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, 
     l0 = __fsub_rn(1.f, lam);
 }
 
-// out = h0*(w0*a + w1*b) + h1*(w0*c + w1*e) in the association/contraction the
-// CPU kernel uses (second product rounded, then fused with the first).
+// out = h0*(w0*a + w1*b) + h1*(w0*c + w1*e).  torch's CPU kernel exists in two
+// compiled instantiations that fuse the multiply-adds differently (<= 1 ulp
+// apart; see oracle/stereo_oracle.py:bilinear_resize):
+//   FOURTERM = false ("separable", canonical): fma(h0, fma(w0,a,w1*b), h1*fma(w0,c,w1*e))
+//   FOURTERM = true  : w_ij = h_i*w_j; fma(w11,e, fma(w10,c, fma(w00,a, w01*b)))
+template <bool FOURTERM>
 __device__ __forceinline__ float bilerp(float a, float b, float c, float e, float w0, float w1, float h0, float h1) {
+    if (FOURTERM) {
+        const float w00 = __fmul_rn(h0, w0), w01 = __fmul_rn(h0, w1), w10 = __fmul_rn(h1, w0), w11 = __fmul_rn(h1, w1);
+        return __fmaf_rn(w11, e, __fmaf_rn(w10, c, __fmaf_rn(w00, a, __fmul_rn(w01, b))));
+    }
     const float top = __fmaf_rn(w0, a, __fmul_rn(w1, b));
     const float bot = __fmaf_rn(w0, c, __fmul_rn(w1, e));
     return __fmaf_rn(h0, top, __fmul_rn(h1, bot));
@@ -70,6 +79,7 @@ __device__ __forceinline__ float blend(float x, float y, float ratio, float one_
 // grid = (ceil(W/128) * ceil(H/ROWS_PER_BLOCK), B); block = 128 threads (one output column each).
 constexpr int PRE_ROWS = 8;
 
+template <bool FOURTERM>
 __global__ void __launch_bounds__(128) decode_resize_kernel(
     const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, const uint8_t* __restrict__ D, int B, int Hs, int Ws,
     int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
                 const float b = __fdiv_rn((float)__ldg(Ln + o01 + c), 255.f);
                 const float cc = __fdiv_rn((float)__ldg(Ln + o10 + c), 255.f);
                 const float e = __fdiv_rn((float)__ldg(Ln + o11 + c), 255.f);
-                rgbL[c] = bilerp(a, b, cc, e, w0, w1, h0, h1);
+                rgbL[c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
                 input[((size_t)n * 6 + c) * plane + opix] = rgbL[c];
             }
 #pragma unroll
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
                 const float b = __fdiv_rn((float)__ldg(Rn + o01 + c), 255.f);
                 const float cc = __fdiv_rn((float)__ldg(Rn + o10 + c), 255.f);
                 const float e = __fdiv_rn((float)__ldg(Rn + o11 + c), 255.f);
-                rgbR[c] = bilerp(a, b, cc, e, w0, w1, h0, h1);
+                rgbR[c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
                 input[((size_t)n * 6 + 3 + c) * plane + opix] = rgbR[c];
             }
             float dv[4];
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
                 const float s = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(r, 255.f), 255.f), __fmul_rn(g, 255.f)), b);
                 dv[k] = __fdiv_rn(s, 1000.f);
             }
-            const float t = __fmul_rn(bilerp(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
+            const float t = __fmul_rn(bilerp<FOURTERM>(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
             target[(size_t)n * plane + opix] = t;
             const bool valid = t > 0.f;
             mask[(size_t)n * plane + opix] = valid ? 1 : 0;

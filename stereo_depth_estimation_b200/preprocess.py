@@ -1,0 +1,161 @@
+"""Device input pipeline: the host-side mirror of the reference's
+``FoundationStereoDataset.__getitem__`` + default collate
+(src/foundation_stereo_depth/dataset.py:184-270,302-311) for raw uint8 images that
+are already on the GPU.  One call produces a whole batch in the reference's
+sample format::
+
+    {"input": [B,6,H,W] f32, "target": [B,1,H,W] f32, "valid_mask": [B,1,H,W] bool}
+
+Augmentation parameters are explicit (``AugmentSampler`` draws them with the
+reference's distributions and draw order, dataset.py:214-246), so a test can
+replay exactly what the reference sampled.  PNG decoding is out of scope.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class ViewAug:
+    """One view's parameters; the same fields as sdn_aug_params (include/sdn.h)."""
+
+    brightness: float = 1.0
+    contrast: float = 1.0
+    saturation: float = 1.0
+    hue: float = 0.0
+    gamma: float = 1.0
+    blur_sigma: float = 0.0
+    noise_std: float = 0.0
+    noise_seed: int = 0
+
+
+class AugmentSampler:
+    """Draws per-view parameters like the reference samplers.
+
+    Distributions and the per-view draw order follow dataset.py:214-246 and
+    248-270: brightness, contrast, saturation ~ U[max(0,1-j), 1+j]; hue ~ U[-j, j];
+    gamma ~ U[max(.1,1-j), 1+j]; blur iff rand < blur_prob with sigma ~ U[0.1,
+    max(sigma_max, 0.1)]; noise_std ~ U[0, max].  Defaults are the CLI defaults of
+    train.py:156-209.  The generator is a host ``numpy`` one (the reference uses the
+    global torch CPU generator; streams cannot be bit-matched across devices)."""
+
+    def __init__(self, brightness_jitter: float = 0.2, contrast_jitter: float = 0.2, saturation_jitter: float = 0.25,
+                 hue_jitter: float = 0.09, gamma_jitter: float = 0.2, noise_std_max: float = 0.05,
+                 blur_prob: float = 0.03, blur_sigma_max: float = 1.0, seed: int = 0) -> None:
+        if not 0.0 <= blur_prob <= 1.0:
+            raise ValueError(f"blur_prob must be in [0, 1], got {blur_prob}")
+        if saturation_jitter < 0.0:
+            raise ValueError(f"saturation_jitter must be >= 0, got {saturation_jitter}")
+        if gamma_jitter < 0.0:
+            raise ValueError(f"gamma_jitter must be >= 0, got {gamma_jitter}")
+        self.j = (brightness_jitter, contrast_jitter, saturation_jitter)
+        self.hue_jitter, self.gamma_jitter = hue_jitter, gamma_jitter
+        self.noise_std_max, self.blur_prob, self.blur_sigma_max = noise_std_max, blur_prob, blur_sigma_max
+        self.rng = np.random.default_rng(seed)
+
+    def _factor(self, jitter: float) -> float:
+        if jitter <= 0.0:
+            return 1.0
+        return float(self.rng.uniform(max(0.0, 1.0 - jitter), 1.0 + jitter))
+
+    def sample_view(self) -> ViewAug:
+        v = ViewAug()
+        v.brightness, v.contrast, v.saturation = (self._factor(j) for j in self.j)
+        v.hue = float(self.rng.uniform(-self.hue_jitter, self.hue_jitter)) if self.hue_jitter > 0 else 0.0
+        if self.gamma_jitter > 0:
+            low = max(0.1, 1.0 - self.gamma_jitter)
+            v.gamma = float(self.rng.uniform(low, max(low, 1.0 + self.gamma_jitter)))
+        if self.blur_prob > 0 and self.blur_sigma_max > 0 and self.rng.random() < self.blur_prob:
+            v.blur_sigma = float(self.rng.uniform(0.1, max(self.blur_sigma_max, 0.1)))
+        v.noise_std = float(self.rng.uniform(0.0, self.noise_std_max)) if self.noise_std_max > 0 else 0.0
+        v.noise_seed = int(self.rng.integers(0, 2**32 - 1))
+        return v
+
+    def sample_batch(self, batch: int) -> list:
+        """2*batch views in (left, right) order per sample, like dataset.py:302-304."""
+        return [self.sample_view() for _ in range(2 * batch)]
+
+
+def pack_aug(views: Sequence[ViewAug]) -> torch.Tensor:
+    """Host (pinned when CUDA is present) uint8 tensor holding the sdn_aug_params array."""
+    arr = (_lib.AugParams * len(views))()
+    for i, v in enumerate(views):
+        arr[i] = _lib.AugParams(v.brightness, v.contrast, v.saturation, v.hue, v.gamma, v.blur_sigma, v.noise_std,
+                                v.noise_seed & 0xFFFFFFFF)
+    raw = np.frombuffer(arr, dtype=np.uint8).copy()
+    t = torch.from_numpy(raw)
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class DevicePreprocessor:
+    """Owns an sdn context used only for its preprocessing workspace."""
+
+    def __init__(self, device: torch.device, max_batch: int, image_size=(240, 320)) -> None:
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("DevicePreprocessor runs on CUDA only; there is no CPU fallback")
+        self.device = torch.device(device)
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        self.max_batch = int(max_batch)
+        lib = _lib.load()
+        self.ctx = c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(lib.sdn_create(ctypes.byref(self.ctx), index, self.max_batch, self.image_size[0],
+                                  self.image_size[1], 0))
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            _lib.load().sdn_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, left: torch.Tensor, right: torch.Tensor, disparity: torch.Tensor,
+                 aug: Optional[Sequence[ViewAug]] = None, fourterm: bool = False,
+                 out: Optional[dict] = None, count_out: Optional[torch.Tensor] = None) -> dict:
+        """left / right / disparity: uint8 [B,Hs,Ws,3] CUDA tensors (HWC, RGB)."""
+        for name, t in (("left", left), ("right", right), ("disparity", disparity)):
+            if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3 or not t.is_cuda:
+                raise ValueError(f"{name} must be a CUDA uint8 tensor [B,Hs,Ws,3], got {t.dtype} {tuple(t.shape)}")
+        if left.shape != right.shape or left.shape != disparity.shape:
+            raise ValueError("left, right and disparity must have the same shape")
+        b, hs, ws, _ = left.shape
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        h, w = self.image_size
+        left, right, disparity = left.contiguous(), right.contiguous(), disparity.contiguous()
+        if out is None:
+            out = {
+                "input": torch.empty((b, 6, h, w), device=self.device, dtype=torch.float32),
+                "target": torch.empty((b, 1, h, w), device=self.device, dtype=torch.float32),
+                "valid_mask": torch.empty((b, 1, h, w), device=self.device, dtype=torch.bool),
+            }
+        aug_dev = None
+        if aug is not None:
+            if len(aug) != 2 * b:
+                raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {len(aug)}")
+            aug_dev = pack_aug(aug).to(self.device, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(
+            _lib.load().sdn_preprocess(
+                self.ctx, left.data_ptr(), right.data_ptr(), disparity.data_ptr(), b, hs, ws,
+                aug_dev.data_ptr() if aug_dev is not None else None,
+                out["input"].data_ptr(), out["target"].data_ptr(), out["valid_mask"].data_ptr(),
+                count_out.data_ptr() if count_out is not None else None,
+                _lib.RESIZE_FOURTERM if fourterm else 0, stream,
+            )
+        )
+        if aug_dev is not None:
+            aug_dev.record_stream(torch.cuda.current_stream(self.device))
+        return out
