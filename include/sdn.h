@@ -50,6 +50,7 @@ int sdn_version(void);
 
 /* Context: workspace for batches up to max_batch at resolution H x W
  * (both multiples of 16, model.py:79-95 pooling/upsampling constraint). */
+#define SDN_CTX_PREPROCESS_ONLY 1u /* flags: allocate only what sdn_preprocess needs */
 int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags);
 int sdn_destroy(sdn_ctx* ctx);
 /* Bytes of device workspace the context holds. */
@@ -114,6 +115,13 @@ int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, cons
  * BN+ReLU, 2 = gradient w.r.t. the pre-BN output (after backward).
  * Copies to a host fp32 buffer of B*H_l*W_l*C_l elements; returns the dims. */
 int sdn_debug_read(sdn_ctx* ctx, int which, int kind, float* host_out, int64_t capacity, int* dims4);
+
+/* Per-op device timing: when enabled every op is bracketed by CUDA events on the
+ * launching stream.  sdn_profile_dump synchronises the device and writes a CSV
+ * "name,layer,calls,total_ms,flops,bytes" (algorithmic flops / bytes of SURVEY 8d
+ * per op) into buf, then clears the records. */
+int sdn_profile_enable(sdn_ctx* ctx, int enable);
+int sdn_profile_dump(sdn_ctx* ctx, char* buf, int64_t capacity);
 
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t sdn_launch_count(const sdn_ctx* ctx);

@@ -17,6 +17,7 @@ NUM_PARAMS = 66
 NUM_BN = 18
 NUM_STAGES = 4
 RESIZE_FOURTERM = 1
+CTX_PREPROCESS_ONLY = 1
 
 # every symbol include/sdn.h declares (tests check that the .so exports them all)
 EXPORTS = (
@@ -34,6 +35,8 @@ EXPORTS = (
     "sdn_count_valid",
     "sdn_preprocess",
     "sdn_debug_read",
+    "sdn_profile_enable",
+    "sdn_profile_dump",
     "sdn_launch_count",
 )
 
@@ -96,6 +99,10 @@ def load() -> ctypes.CDLL:
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint, c_void_p]
+    lib.sdn_profile_enable.restype = c_int
+    lib.sdn_profile_enable.argtypes = [c_void_p, c_int]
+    lib.sdn_profile_dump.restype = c_int
+    lib.sdn_profile_dump.argtypes = [c_void_p, ctypes.c_char_p, c_int64]
     lib.sdn_debug_read.restype = c_int
     lib.sdn_debug_read.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), c_int64, POINTER(c_int)]
     _lib = lib
@@ -108,6 +115,19 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().sdn_last_error()
         raise RuntimeError("libsdn_b200: " + (msg.decode("utf-8", "replace") if msg else f"error {rc}"))
+
+
+def profile_dump(ctx) -> list:
+    """Parse sdn_profile_dump's CSV into a list of dicts."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().sdn_profile_dump(ctx, buf, len(buf)))
+    rows = []
+    lines = buf.value.decode().strip().splitlines()
+    for line in lines[1:]:
+        name, layer, calls, ms, flops, nbytes = line.split(",")
+        rows.append({"name": name, "layer": int(layer), "calls": int(calls), "ms": float(ms), "flops": float(flops),
+                     "bytes": float(nbytes)})
+    return rows
 
 
 def stage_param_range(stage: int) -> tuple[int, int]:

@@ -192,8 +192,45 @@ struct sdn_ctx {
     float* bn_rv[SDN_NUM_BN] = {};
     int64_t* bn_nbt[SDN_NUM_BN] = {};
     bool have_params = false, have_forward_train = false;
+    bool pre_only = false;  // SDN_CTX_PREPROCESS_ONLY: no network workspace
     int accumulate = 0;
     int64_t launches = 0;
+    // optional per-op timing (CUDA events on the launching stream)
+    bool prof = false;
+    struct ProfRec {
+        const char* name;
+        int layer;
+        cudaEvent_t a, b;
+        double flops, bytes;
+    };
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+};
+
+// Times everything enqueued on `st` during its lifetime when profiling is on.
+struct ProfScope {
+    sdn_ctx* c;
+    cudaStream_t st;
+    int idx = -1;
+    ProfScope(sdn_ctx* c_, cudaStream_t st_, const char* name, int layer, double flops, double bytes) : c(c_), st(st_) {
+        if (!c->prof) return;
+        sdn_ctx::ProfRec r{name, layer, c->next_event(), c->next_event(), flops, bytes};
+        cudaEventRecord(r.a, st);
+        idx = (int)c->recs.size();
+        c->recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(c->recs[idx].b, st);
+    }
 };
 
 static const int BWD_BLOCKS = 592;  // 4 x 148
@@ -436,9 +473,9 @@ static int plan_and_alloc(sdn_ctx* c) {
             a.C = C; a.H = lvl_h(c, lvl); a.W = lvl_w(c, lvl);
             carve(cur, a.elems(B) * sizeof(bf16), (void**)&a.p);
         };
-        act(c->x0, 64, 1);
         size_t wg_off = 0;
-        for (int b = 0; b < 9; ++b) {
+        if (!c->pre_only) act(c->x0, 64, 1);
+        for (int b = 0; b < 9 && !c->pre_only; ++b) {
             for (int h = 0; h < 2; ++h) {
                 ConvL& L = c->conv[2 * b + h];
                 L.cin = h == 0 ? kBlockCin[b] : kBlockCout[b];
@@ -466,7 +503,7 @@ static int plan_and_alloc(sdn_ctx* c) {
                 wg_off += (size_t)kdim * L.cout;
             }
         }
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4 && !c->pre_only; ++k) {
             UpL& U = c->up[k];
             U.cin = kBlockCout[4 + k];       // 512, 256, 128, 64
             U.cout = U.cin / 2;
@@ -484,7 +521,7 @@ static int plan_and_alloc(sdn_ctx* c) {
         // contiguous fp32 weight-gradient workspace (one memset per backward)
         carve(cur, wg_off * sizeof(float) + 1024, (void**)&c->wg_all);
         c->wg_all_bytes = wg_off * sizeof(float) + 1024;
-        if (pass == 1) {
+        if (pass == 1 && !c->pre_only) {
             float* w = c->wg_all;
             for (int i = 0; i < 18; ++i) {
                 ConvL& L = c->conv[i];
@@ -511,6 +548,7 @@ static int plan_and_alloc(sdn_ctx* c) {
             CUDA_OK(cudaMemset(c->ws, 0, c->ws_bytes));
         }
     }
+    if (c->pre_only) return 0;
     // wiring of conv inputs
     for (int b = 0; b < 9; ++b) {
         ConvL& L0 = c->conv[2 * b];
@@ -597,6 +635,7 @@ static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
 
 // bf16 operand cache <- fp32 parameters
 static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
+    ProfScope ps(c, st, "pack_weights", 0, 0.0, 7763938.0 * (4 + 2) * (training ? 2 : 1));
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
         const float* w = c->params[L.p_w];
@@ -647,6 +686,7 @@ static int run_bn_relu(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
 
 static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, int B, int training, int dirty,
                         cudaStream_t st) {
+    if (c->pre_only) return fail("sdn_forward: context was created with SDN_CTX_PREPROCESS_ONLY");
     if (!c->have_params) return fail("sdn_forward: call sdn_set_params first");
     SDN_OK(prepare_batch(c, B));
     if (dirty) SDN_OK(pack_params(c, training != 0, st));
@@ -660,15 +700,31 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
         }
     }
     const int H = c->H, W = c->W;
-    im2col_first_kernel<<<ew_grid(c, (long long)B * H * W * 8, 256), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
-    ++c->launches;
+    {
+        const double px = (double)B * H * W;
+        ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + 64 * 2));
+        im2col_first_kernel<<<ew_grid(c, (long long)B * H * W * 8, 256), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
+        ++c->launches;
+    }
     CUDA_OK(cudaGetLastError());
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
-        if (i >= 10 && i % 2 == 0) SDN_OK(launch_cg(c, c->up[(i - 10) / 2].fprop, st));
+        if (i >= 10 && i % 2 == 0) {
+            UpL& U = c->up[(i - 10) / 2];
+            const double px = (double)B * U.src->H * U.src->W;
+            ProfScope ps(c, st, "convT_fprop", 100 + (i - 10) / 2, 2.0 * px * U.cin * 4 * U.cout,
+                         px * (U.cin + 4 * U.cout) * 2);
+            SDN_OK(launch_cg(c, U.fprop, st));
+        }
         GemmOp op = L.fprop;
         op.p.flags = training ? CG_STATS : 0;
-        SDN_OK(launch_cg(c, op, st));
+        {
+            const double px = (double)B * L.y.H * L.y.W;
+            ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+            SDN_OK(launch_cg(c, op, st));
+        }
+        ProfScope ps(c, st, "bn_relu_pool", i, 0.0,
+                     (double)B * L.y.H * L.y.W * L.cout * 2 * (L.pooled_out ? 2.25 : 2.0));
         if (training) {
             const double count = (double)B * L.y.H * L.y.W;
             bn_finalize_train_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(
@@ -680,6 +736,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     }
     if (disp != nullptr) {
         const long long npix = (long long)B * H * W;
+        ProfScope ps(c, st, "head_fwd", 0, 0.0, (double)npix * (64 + (logvar ? 8 : 4)));
         head_kernel<0><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63],
                                                               c->params[64], c->params[65], disp, logvar, nullptr,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -722,8 +779,18 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
 
 static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
     ConvL& L = c->conv[i];
-    SDN_OK(bn_backward(c, L, B, st));
-    SDN_OK(launch_wg(c, L.wgrad, st));
+    const double px = (double)B * L.y.H * L.y.W;
+    {
+        // reduce: y + g (+ gp/4); apply: y + g (+ gp/4) + dy
+        ProfScope ps(c, st, "bn_bwd", i, 0.0, px * L.cout * 2 * (L.pooled_out ? 5.5 : 5.0));
+        SDN_OK(bn_backward(c, L, B, st));
+    }
+    {
+        ProfScope ps(c, st, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+        SDN_OK(launch_wg(c, L.wgrad, st));
+    }
+    ProfScope ps2(c, st, L.has_dgrad ? "conv_dgrad" : "grad_unpack", i, L.has_dgrad ? 2.0 * px * L.cout * 9 * L.cin : 0.0,
+                  L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
     if (c->grads[L.p_w] != nullptr) {
         const int n = 9 * L.cin * L.cout;
         unpack_grad_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
@@ -739,9 +806,17 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
     UpL& U = c->up[k];
     const long long npix = (long long)B * U.gu.H * U.gu.W;
     dim3 g(U.cout / 8, (unsigned)std::max(1LL, std::min((npix + 255) / 256, (long long)(c->num_sms * 2))));
-    colsum_kernel<<<g, 256, 0, st>>>(U.gu.p, npix, U.cout, U.bg, 0);
-    ++c->launches;
-    SDN_OK(launch_wg(c, U.wgrad, st));
+    const double pxin = (double)B * U.src->H * U.src->W;
+    {
+        ProfScope ps(c, st, "convT_bias_grad", 100 + k, 0.0, (double)npix * U.cout * 2);
+        colsum_kernel<<<g, 256, 0, st>>>(U.gu.p, npix, U.cout, U.bg, 0);
+        ++c->launches;
+    }
+    {
+        ProfScope ps(c, st, "convT_wgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
+        SDN_OK(launch_wg(c, U.wgrad, st));
+    }
+    ProfScope ps2(c, st, "convT_dgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
     if (c->grads[U.p_w] != nullptr) {
         const int n = 4 * U.cin * U.cout;
         unpack_grad_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
@@ -784,7 +859,6 @@ const char* sdn_last_error(void) { return g_err.c_str(); }
 int sdn_version(void) { return 100; }
 
 int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags) {
-    (void)flags;
     if (out == nullptr) return fail("sdn_create: out is NULL");
     if (H % 16 != 0 || W % 16 != 0 || H < 16 || W < 16) return fail("H and W must be positive multiples of 16 (got %dx%d)", H, W);
     if (max_batch < 1) return fail("max_batch must be >= 1");
@@ -800,6 +874,7 @@ int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned 
     sdn_ctx* c = new sdn_ctx();
     c->device = device; c->maxB = max_batch; c->H = H; c->W = W;
     c->num_sms = prop.multiProcessorCount;
+    c->pre_only = (flags & SDN_CTX_PREPROCESS_ONLY) != 0;
     int r = plan_and_alloc(c);
     if (r != 0) { if (c->ws) cudaFree(c->ws); delete c; return r; }
     *out = c;
@@ -849,6 +924,7 @@ int sdn_backward_begin(sdn_ctx* c, const float* g_disp, const float* g_logvar, i
     CUDA_OK(cudaSetDevice(c->device));
     SDN_OK(backward_prologue(c, accumulate, st));
     const long long npix = (long long)c->B * c->H * c->W;
+    ProfScope ps(c, st, "head_bwd", 0, 0.0, (double)npix * (64 + 8 + 64));
     head_kernel<1><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], nullptr, nullptr, g_disp, g_logvar, nullptr,
                                                           nullptr, nullptr, nullptr, nullptr, c->conv[17].ga.p,
@@ -893,6 +969,7 @@ int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* 
         n_norm_dev = c->n_local;  // zero -> gradients are zero and unused
     }
     // the gradient buffer of dec1's output doubles as scratch on the metrics-only path
+    ProfScope ps(c, st, "head_loss", 0, 0.0, (double)npix * (64 + 4 + 1 + 64));
     head_kernel<2><<<ew_grid(c, npix, 256), 256, 0, st>>>(c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], disp, logvar, nullptr, nullptr, target, mask,
                                                           n_norm_dev, sums4, count, c->conv[17].ga.p, c->head_grads,
@@ -955,6 +1032,8 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     const int parts = xblocks * yblocks;
     if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
     const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
+    // 3 uint8 sources read + fp32 input/target + u8 mask written per sample
+    ProfScope ps(c, st, "preprocess", 0, 0.0, (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
     if (flags & SDN_RESIZE_FOURTERM)
         decode_resize_kernel<true><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
                                                                    target, mask, valid_count, aug,
@@ -973,6 +1052,42 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdn_profile_enable(sdn_ctx* c, int enable) {
+    if (c == nullptr) return fail("sdn_profile_enable: NULL ctx");
+    c->prof = enable != 0;
+    c->recs.clear();
+    c->ev_used = 0;
+    return 0;
+}
+
+// CSV "name,layer,calls,total_ms,flops,bytes" aggregated per (name, layer) since enable; resets the records.
+int sdn_profile_dump(sdn_ctx* c, char* buf, int64_t capacity) {
+    if (c == nullptr || buf == nullptr || capacity < 64) return fail("sdn_profile_dump: bad argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    struct Agg { const char* name; int layer; int calls; double ms, flops, bytes; };
+    std::vector<Agg> aggs;
+    for (const auto& r : c->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        Agg* hit = nullptr;
+        for (auto& a : aggs) if (a.layer == r.layer && strcmp(a.name, r.name) == 0) { hit = &a; break; }
+        if (!hit) { aggs.push_back(Agg{r.name, r.layer, 0, 0.0, 0.0, 0.0}); hit = &aggs.back(); }
+        hit->calls += 1; hit->ms += ms; hit->flops += r.flops; hit->bytes += r.bytes;
+    }
+    std::string out = "name,layer,calls,total_ms,flops,bytes\n";
+    char line[256];
+    for (const auto& a : aggs) {
+        snprintf(line, sizeof line, "%s,%d,%d,%.6f,%.6e,%.6e\n", a.name, a.layer, a.calls, a.ms, a.flops, a.bytes);
+        out += line;
+    }
+    c->recs.clear();
+    c->ev_used = 0;
+    if ((int64_t)out.size() + 1 > capacity) return fail("sdn_profile_dump: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

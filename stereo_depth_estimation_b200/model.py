@@ -315,6 +315,12 @@ class StereoUNet(nn.Module):
         )
         return buf.view(dims[0], dims[1], dims[2], dims[3])
 
+    def profile_enable(self, enable: bool = True) -> None:
+        _lib.check(_lib.load().sdn_profile_enable(self._engine.ctx, 1 if enable else 0))
+
+    def profile_dump(self) -> list:
+        return _lib.profile_dump(self._engine.ctx)
+
     def launch_count(self) -> int:
         eng = self._engine
         return int(_lib.load().sdn_launch_count(eng.ctx)) if eng.ctx is not None else 0

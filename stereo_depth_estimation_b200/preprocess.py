@@ -108,7 +108,7 @@ class DevicePreprocessor:
         self.ctx = c_void_p()
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(lib.sdn_create(ctypes.byref(self.ctx), index, self.max_batch, self.image_size[0],
-                                  self.image_size[1], 0))
+                                  self.image_size[1], _lib.CTX_PREPROCESS_ONLY))
 
     def close(self) -> None:
         if getattr(self, "ctx", None) is not None and self.ctx:
@@ -120,6 +120,15 @@ class DevicePreprocessor:
             self.close()
         except Exception:
             pass
+
+    def profile_enable(self, enable: bool = True) -> None:
+        _lib.check(_lib.load().sdn_profile_enable(self.ctx, 1 if enable else 0))
+
+    def profile_dump(self) -> list:
+        return _lib.profile_dump(self.ctx)
+
+    def launch_count(self) -> int:
+        return int(_lib.load().sdn_launch_count(self.ctx))
 
     def __call__(self, left: torch.Tensor, right: torch.Tensor, disparity: torch.Tensor,
                  aug: Optional[Sequence[ViewAug]] = None, fourterm: bool = False,

@@ -1,0 +1,411 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI via the Python
+mirror, against the oracle and the committed golden fixtures.
+
+Tolerances (stated here, see DESIGN.md "Parity"):
+  * decode / resize / mask / valid count : bit-exact
+  * augmentation (explicit parameters)   : <= 1e-5 abs (transcendentals differ by ulps)
+  * eval-mode forward (live-view path)   : max|err| / max|ref| <= 1e-2  (north_star)
+  * train-mode forward, bf16 storage     : rel-L2 <= 1.5e-2, loss <= 1e-3 relative
+  * every backward kernel on ITS OWN inputs vs torch fp32: wgrad <= 1e-4, dgrad /
+    BatchNorm-backward <= 6e-3 rel-L2 (one bf16 rounding of the output)
+  * end-to-end gradients vs fp32 autograd: no worse than 1.5x torch's own bf16-autocast
+    drift on the same batch (+2e-2), measured in the same test
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stereo_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def make_batch(dev, b, h, w, seed=123, scale=1.5):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, 6, h, w, generator=g)
+    t = torch.rand(b, 1, h, w, generator=g) * scale
+    t[:, :, : h // 4, : w // 4] = 0.0
+    return {"input": x.to(dev), "target": t.to(dev), "valid_mask": (t > 0).to(dev)}
+
+
+def fresh_model(dev, seed=42):
+    from stereo_depth_estimation_b200 import StereoUNet
+
+    torch.manual_seed(seed)
+    model = StereoUNet().to(dev)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return model, sd
+
+
+def synth_sources(rng, b, hs, ws):
+    L = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    R = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    D = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    D[..., 0] = rng.integers(0, 4, (b, hs, ws))
+    D[rng.random((b, hs, ws)) < 0.1] = 0
+    return L, R, D
+
+
+# ------------------------------------------------------------------ preprocess
+@pytest.mark.parametrize("name", ["sample_exact", "sample_ragged", "sample_up", "sample_same"])
+def test_preprocess_matches_reference_fixture_bit_exact(dev, name):
+    """The fixtures are outputs of the real reference (small images -> its 'fourterm' CPU kernel)."""
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor
+
+    f = np.load(os.path.join(GOLDEN, name + ".npz"))
+    h, w = (int(v) for v in f["out_hw"])
+    pre = DevicePreprocessor(dev, 1, (h, w))
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    args = [torch.from_numpy(f[k][None]).to(dev) for k in ("left", "right", "disp")]
+    out = pre(*args, fourterm=True, count_out=cnt)
+    assert np.array_equal(out["input"][0].cpu().numpy(), f["input"])
+    assert np.array_equal(out["target"][0].cpu().numpy(), f["target"])
+    assert np.array_equal(out["valid_mask"][0].cpu().numpy(), f["valid_mask"])
+    assert out["valid_mask"].dtype == torch.bool and out["input"].dtype == torch.float32
+    assert int(cnt.item()) == int(f["valid_mask"].sum())
+    sep = pre(*args)  # canonical ordering == oracle default
+    ref = so.make_sample(f["left"], f["right"], f["disp"], (h, w))
+    assert np.array_equal(sep["input"][0].cpu().numpy(), ref["input"])
+    assert np.array_equal(sep["target"][0].cpu().numpy(), ref["target"])
+
+
+def test_preprocess_full_size_bit_exact(dev):
+    """BASELINE.json config 4 shape (540x960 -> 240x320), ragged batch of 3."""
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor
+
+    rng = np.random.default_rng(5)
+    L, R, D = synth_sources(rng, 3, 540, 960)
+    D[1] = 0  # a sample with no valid pixel at all
+    pre = DevicePreprocessor(dev, 4, (240, 320))
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    out = pre(torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev), torch.from_numpy(D).to(dev), count_out=cnt)
+    total = 0
+    for i in range(3):
+        ref = so.make_sample(L[i], R[i], D[i], (240, 320))
+        assert np.array_equal(out["input"][i].cpu().numpy(), ref["input"])
+        assert np.array_equal(out["target"][i].cpu().numpy(), ref["target"])
+        assert np.array_equal(out["valid_mask"][i].cpu().numpy(), ref["valid_mask"])
+        total += int(ref["valid_mask"].sum())
+    assert int(cnt.item()) == total
+    assert not out["valid_mask"][1].any()
+    # horizontal scale 3.0 is pure point sampling of column 3x+1
+    plain = (L[0, :, 1::3, :].astype(np.float32) / np.float32(255.0))
+    assert out["input"].shape == (3, 6, 240, 320) and plain.shape[1] == 320
+
+
+def test_preprocess_decode_kats(dev):
+    """reference tests/test_dataset.py:31-35,38-61 through the device kernel."""
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor
+
+    src = np.full((1, 2, 4), 1.5, dtype=np.float32)
+    enc = so.encode_disparity(src)
+    zeros = np.zeros_like(enc)
+    pre = DevicePreprocessor(dev, 1, (16, 32))  # the library needs multiples of 16
+    big = np.repeat(np.repeat(enc, 8, axis=1), 4, axis=2)  # 16 x 16 constant 1.5 px
+    out = pre(torch.from_numpy(np.zeros_like(big)).to(dev), torch.from_numpy(np.zeros_like(big)).to(dev),
+              torch.from_numpy(big).to(dev))
+    np.testing.assert_allclose(out["target"].cpu().numpy(), 3.0, atol=1e-3)  # width doubled -> disparity doubled
+    white = np.full((1, 16, 32, 3), 255, dtype=np.uint8)
+    out = pre(torch.from_numpy(white).to(dev), torch.from_numpy(white).to(dev), torch.from_numpy(white).to(dev))
+    assert np.all(out["target"].cpu().numpy() == np.float32(16646.654))
+    assert np.all(out["input"].cpu().numpy() == np.float32(1.0))
+    _ = zeros
+
+
+def test_augment_matches_oracle(dev):
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor, ViewAug
+
+    rng = np.random.default_rng(9)
+    b, h, w = 3, 48, 64
+    L, R, D = synth_sources(rng, b, 108, 192)
+    L[0, :20, :40] = 128  # gray patch: maxc == minc branch
+    views = [ViewAug(1.1, 0.85, 1.2, 0.05, 0.9), ViewAug(0.8, 1.2, 0.8, -0.09, 1.2, blur_sigma=0.7),
+             ViewAug(), ViewAug(1.2, 0.8, 1.25, 0.5, 0.8, blur_sigma=1.0),
+             ViewAug(0.9, 1.1, 0.0, -0.5, 1.0), ViewAug(1.0, 1.0, 1.0, 0.0, 1.0, blur_sigma=0.1)]
+    pre = DevicePreprocessor(dev, b, (h, w))
+    out = pre(torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev), torch.from_numpy(D).to(dev), aug=views)
+    for i in range(b):
+        aug = [dict(brightness=v.brightness, contrast=v.contrast, saturation=v.saturation, hue=v.hue, gamma=v.gamma,
+                    blur_sigma=v.blur_sigma) for v in views[2 * i: 2 * i + 2]]
+        ref = so.make_sample(L[i], R[i], D[i], (h, w), aug=aug)
+        np.testing.assert_allclose(out["input"][i].cpu().numpy(), ref["input"], atol=1e-5, rtol=0)
+        assert np.array_equal(out["target"][i].cpu().numpy(), ref["target"])  # augmentation never touches the target
+
+
+def test_augment_noise_statistics(dev):
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor, ViewAug
+
+    rng = np.random.default_rng(2)
+    b, h, w = 2, 240, 320
+    L, R, D = synth_sources(rng, b, 240, 320)
+    pre = DevicePreprocessor(dev, b, (h, w))
+    src = [torch.from_numpy(a).to(dev) for a in (L, R, D)]
+    base = pre(*src, aug=[ViewAug() for _ in range(2 * b)])["input"].clone()
+    noisy = pre(*src, aug=[ViewAug(noise_std=0.05, noise_seed=10 + k) for k in range(2 * b)])["input"]
+    inner = (base > 0.25) & (base < 0.75)
+    d = (noisy - base)[inner]
+    assert abs(d.mean().item()) < 5e-4 and abs(d.std().item() - 0.05) < 5e-4
+    assert noisy.min().item() >= 0.0 and noisy.max().item() <= 1.0
+    again = pre(*src, aug=[ViewAug(noise_std=0.05, noise_seed=10 + k) for k in range(2 * b)])["input"]
+    assert torch.equal(noisy, again)  # counter-based generator: same seed, same noise
+    v0, v1 = (noisy - base)[0, :3][inner[0, :3]], (noisy - base)[0, 3:][inner[0, 3:]]
+    n = min(v0.numel(), v1.numel())
+    assert abs(torch.corrcoef(torch.stack([v0[:n], v1[:n]]))[0, 1].item()) < 0.02  # L / R independent
+
+
+# --------------------------------------------------------------------- forward
+@pytest.mark.parametrize("b,h,w", [(1, 240, 320), (3, 64, 96), (2, 32, 48)])
+def test_forward_eval_matches_oracle(dev, b, h, w):
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, b, h, w)
+    model.eval()
+    with torch.inference_mode():
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+        disp_only = model(batch["input"])
+    rd, rl = so.model_forward(sd, batch["input"], False, True)
+    assert disp.shape == (b, 1, h, w) and disp.dtype == torch.float32
+    assert torch.equal(disp, disp_only)
+    assert (disp - rd).abs().max().item() / rd.abs().max().item() <= 1e-2
+    assert (logvar - rl).abs().max().item() / rl.abs().max().item() <= 1e-2
+    assert disp.min().item() >= 0.0 and logvar.min().item() >= -6.0 and logvar.max().item() <= 3.0
+
+
+def test_forward_eval_golden_fixture(dev):
+    """model.npz was produced by the real reference (seed 42, trained-one-step BN buffers)."""
+    f = np.load(os.path.join(GOLDEN, "model.npz"))
+    model, _ = fresh_model(dev)
+    x = torch.from_numpy(f["input"]).to(dev)
+    model.train()
+    with torch.no_grad():
+        d_t, l_t = model(x, return_uncertainty=True)   # updates the BN buffers like the reference run did
+    assert rel(d_t.cpu(), torch.from_numpy(f["disp_train"])) < 2.5e-2   # B=2, 32x48: 12 samples per channel in the bottleneck
+    model.eval()
+    with torch.inference_mode():
+        d_e, l_e = model(x, return_uncertainty=True)
+    assert rel(d_e.cpu(), torch.from_numpy(f["disp_eval"])) < 2.5e-2
+    assert rel(l_e.cpu(), torch.from_numpy(f["logvar_eval"])) < 5e-2
+    for k, v in model.state_dict().items():
+        if "num_batches" in k:
+            assert int(v.item()) == 1
+
+
+@pytest.mark.parametrize("b,h,w", [(4, 240, 320), (3, 64, 96)])
+def test_forward_train_matches_oracle(dev, b, h, w):
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, b, h, w)
+    model.train()
+    with torch.no_grad():
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+    new = {}
+    rd, rl = so.model_forward(sd, batch["input"], True, True, new)
+    assert rel(disp, rd) <= 1.5e-2 and rel(logvar, rl) <= 3e-2
+    loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
+    rloss, _ = so.loss_and_sums(rd, rl, batch["target"], batch["valid_mask"])
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3
+    cur = model.state_dict()
+    for k, v in new.items():
+        if "running" in k:
+            assert rel(cur[k], v) < 2e-2, k
+        elif "num_batches" in k:
+            assert int(cur[k].item()) == int(v.item())
+
+
+# -------------------------------------------------------------------- backward
+def _nchw(model, which, kind, dev):
+    return model.debug_activation(which, kind).to(dev).permute(0, 3, 1, 2).contiguous()
+
+
+def test_backward_kernels_isolated(dev):
+    """Each backward kernel against torch fp32 on the kernel's own inputs."""
+    b, h, w = 3, 64, 96
+    model, _ = fresh_model(dev)
+    batch = make_batch(dev, b, h, w)
+    model.train()
+    disp, logvar = model(batch["input"], return_uncertainty=True)
+    loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
+    loss.backward()
+    y = [_nchw(model, i, 0, dev) for i in range(18)]
+    a = [_nchw(model, i, 1, dev) for i in range(18)]
+    dy = [_nchw(model, i, 2, dev) for i in range(18)]
+    ga = [_nchw(model, i, 3, dev) for i in range(18)]
+    u = [_nchw(model, 100 + k, 0, dev) for k in range(4)]
+    gu = [_nchw(model, 100 + k, 3, dev) for k in range(4)]
+    params = dict(model.named_parameters())
+    wname = lambda i: f"{so.BLOCKS[i // 2]}.block.{0 if i % 2 == 0 else 3}.weight"  # noqa: E731
+    bnname = lambda i: f"{so.BLOCKS[i // 2]}.block.{1 if i % 2 == 0 else 4}"  # noqa: E731
+
+    def layer_input(i):
+        if i == 0:
+            return batch["input"]
+        if i % 2 == 1:
+            return a[i - 1]
+        if i <= 8:
+            return F.max_pool2d(a[i - 1], 2)
+        k = (i - 10) // 2
+        return torch.cat([u[k], a[7 - 2 * k]], 1)
+
+    for i in range(18):
+        wt = params[wname(i)]
+        xin = layer_input(i)
+        wg_ref = torch.nn.grad.conv2d_weight(xin, wt.shape, dy[i], padding=1)
+        assert rel(wt.grad, wg_ref) < (6e-3 if i == 0 else 1e-4), f"wgrad {i}"  # layer 0 rounds its fp32 input to bf16
+        if i > 0:
+            gin = torch.nn.grad.conv2d_input(xin.shape, wt, dy[i], padding=1)
+            if i % 2 == 1:
+                assert rel(ga[i - 1], gin) < 6e-3, f"dgrad {i}"
+            elif i >= 10:
+                k = (i - 10) // 2
+                c = gu[k].shape[1]
+                assert rel(gu[k], gin[:, :c]) < 6e-3 and rel(ga[7 - 2 * k], gin[:, c:]) < 6e-3, f"dgrad {i}"
+        if i not in (1, 3, 5, 7):  # pooled outputs: arg-max ties on bf16 values, checked end to end
+            yy = y[i].clone().requires_grad_(True)
+            z = F.batch_norm(yy, None, None, params[bnname(i) + ".weight"], params[bnname(i) + ".bias"], True, 0.1, 1e-5)
+            (F.relu(z) * ga[i]).sum().backward()
+            assert rel(dy[i], yy.grad) < 6e-3, f"bn backward {i}"
+    for k in range(4):
+        lvl = 4 - k
+        wt, bt = params[f"up{lvl}.weight"], params[f"up{lvl}.bias"]
+        src = a[9 + 2 * k].clone().requires_grad_(True)
+        wl, bl = wt.detach().clone().requires_grad_(True), bt.detach().clone().requires_grad_(True)
+        (F.conv_transpose2d(src, wl, bl, stride=2) * gu[k]).sum().backward()
+        assert rel(wt.grad, wl.grad) < 1e-4 and rel(bt.grad, bl.grad) < 1e-4
+        assert rel(ga[9 + 2 * k], src.grad) < 6e-3
+
+
+def test_gradients_no_worse_than_torch_bf16_autocast(dev):
+    b, h, w = 4, 128, 160
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, b, h, w)
+    model.train()
+    disp, logvar = model(batch["input"], return_uncertainty=True)
+    loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
+    loss.backward()
+    ours = {k: p.grad.clone() for k, p in model.named_parameters()}
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        leaves = {k: sd[k].clone().requires_grad_(True) for k in so.param_keys(sd)}
+        work = dict(sd)
+        work.update(leaves)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            rd, rl = so.model_forward(work, batch["input"], True, True, {})
+        rloss, _ = so.loss_and_sums(rd.float(), rl.float(), batch["target"], batch["valid_mask"])
+        rloss.backward()
+        grads[mode] = {k: v.grad for k, v in leaves.items()}
+    for k in ours:
+        e_ours = rel(ours[k], grads["fp32"][k])
+        e_torch = rel(grads["bf16"][k], grads["fp32"][k])
+        assert e_ours <= 1.5 * e_torch + 2e-2, (k, e_ours, e_torch)
+        cos = F.cosine_similarity(ours[k].flatten().double(), grads["fp32"][k].flatten().double(), dim=0).item()
+        assert cos > 0.8, (k, cos)
+    for k in ("disparity_head.weight", "logvar_head.weight", "dec1.block.4.weight", "dec1.block.4.bias"):
+        assert rel(ours[k], grads["fp32"][k]) < 2e-2, k
+
+
+# ------------------------------------------------------------------ fused step
+def test_fused_step_matches_module_path_and_oracle_sums(dev):
+    from stereo_depth_estimation_b200.step import FusedStep
+
+    b, h, w = 3, 64, 96
+    batch = make_batch(dev, b, h, w)
+    model_a, sd = fresh_model(dev)
+    model_a.train()
+    d, lv = model_a(batch["input"], return_uncertainty=True)
+    loss, sums = so.loss_and_sums(d, lv, batch["target"], batch["valid_mask"])
+    loss.backward()
+    model_b, _ = fresh_model(dev)
+    step = FusedStep(model_b, optimizer=None)
+    n = step.train_step(batch)
+    got = step.read_metrics()
+    assert n == sums["count"] == got["count"]
+    for k in ("nll", "abs", "sq", "sigma"):
+        assert got[k] == pytest.approx(sums[k], rel=2e-4), k
+    for (ka, pa), (kb, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert rel(pb.grad, pa.grad) < 2e-3, ka   # same kernels; only the loss seed differs (fused vs torch ops)
+
+
+def test_fused_step_skips_batch_without_valid_pixels(dev):
+    from stereo_depth_estimation_b200.step import FusedStep
+
+    model, sd = fresh_model(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    batch = make_batch(dev, 2, 32, 48)
+    batch["valid_mask"] = torch.zeros_like(batch["valid_mask"])
+    step = FusedStep(model, opt)
+    assert step.train_step(batch) == 0
+    for k, v in model.state_dict().items():
+        if so.is_param_key(k):
+            assert torch.equal(v, sd[k]), k        # no optimizer step (train.py:331-332)
+    assert step.read_metrics()["count"] == 0
+    nan_batch = make_batch(dev, 2, 32, 48)
+    nan_batch["target"][0, 0, 20, 20] = float("nan")
+    n = step.train_step(nan_batch)
+    assert n == int((nan_batch["valid_mask"] & torch.isfinite(nan_batch["target"])).sum().item())
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_run_epoch_tracks_oracle_curve(dev):
+    """A short synthetic training curve: fused CUDA steps vs the fp32 oracle, same data."""
+    from stereo_depth_estimation_b200.step import run_epoch
+
+    b, h, w, steps = 4, 64, 96, 12
+    batches = [make_batch(dev, b, h, w, seed=300 + i) for i in range(steps)]
+    model, sd = fresh_model(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    logged = []
+    ours = []
+    osd = {k: v.clone() for k, v in sd.items()}
+    oopt = so.AdamWState()
+    ref = []
+    gs = 0
+    for i in range(0, steps, 4):
+        m, gs = run_epoch(model, batches[i:i + 4], dev, optimizer=opt, global_step=gs, log_every_batches=2,
+                          log_metrics=lambda d, step: logged.append((step, d)))
+        ours.append(m["loss"])
+        ref.append(so.run_epoch(osd, batches[i:i + 4], oopt)["loss"])
+    assert gs == steps and len(logged) == steps // 2
+    assert set(logged[0][1]) == {"train_loss_step", "train_nll_step", "train_mae_step", "train_rmse_step", "train_sigma_step"}
+    for a_, r_ in zip(ours, ref):
+        assert a_ == pytest.approx(r_, rel=3e-2)
+    assert ours[-1] < ours[0]
+    val, _ = run_epoch(model, batches[:2], dev, optimizer=None)
+    oval = so.run_epoch(osd, batches[:2], None)
+    assert val["mae"] == pytest.approx(oval["mae"], rel=5e-2)
+
+
+def test_checkpoint_round_trip_and_compat(dev):
+    from stereo_depth_estimation_b200 import StereoUNet, load_state_dict_compat
+
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, 1, 32, 48)
+    model.eval()
+    with torch.inference_mode():
+        want = model(batch["input"])
+    legacy = {k.replace("disparity_head", "output_head"): v.cpu() for k, v in sd.items() if "logvar_head" not in k}
+    other = StereoUNet().to(dev)
+    missing, unexpected = load_state_dict_compat(other, legacy)
+    assert missing == [] and unexpected == []
+    other.eval()
+    with torch.inference_mode():
+        got = other(batch["input"])
+    assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 6, 30, 48, device=dev))
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 6, 32, 48))
