@@ -860,7 +860,9 @@ int sdn_version(void) { return 100; }
 
 int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags) {
     if (out == nullptr) return fail("sdn_create: out is NULL");
-    if (H % 16 != 0 || W % 16 != 0 || H < 16 || W < 16) return fail("H and W must be positive multiples of 16 (got %dx%d)", H, W);
+    const bool pre_only_req = (flags & SDN_CTX_PREPROCESS_ONLY) != 0;
+    if (H < 1 || W < 1) return fail("H and W must be positive (got %dx%d)", H, W);
+    if (!pre_only_req && (H % 16 != 0 || W % 16 != 0)) return fail("H and W must be positive multiples of 16 (got %dx%d)", H, W);
     if (max_batch < 1) return fail("max_batch must be >= 1");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
