@@ -54,6 +54,7 @@ struct alignas(64) ConvGemmParams {
     int n_total;                    // n_tiles * BLOCK_N
     int flags;
     int stages;
+    int a_stage_bytes;      // HALO: bytes of one (TH+2) x TW halo box, 1024-aligned
     const float* bias;      // [n_total] or nullptr; added before ReLU
     float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS
 };
@@ -77,9 +78,19 @@ struct CgCfg {
     static constexpr int smem_bytes(int stages) {
         return 1024 + stages * STAGE_BYTES + D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
     }
+    // HALO: one stage = one halo A box + the three vertical-tap weight blocks
+    static constexpr int smem_bytes_halo(int stages, int a_stage_bytes) {
+        return 1024 + stages * (a_stage_bytes + 3 * B_BYTES) + D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
+    }
 };
 
-template <int SWA, int BLOCK_N>
+// HALO = true (3x3 convs, one image per box, TW % 8 == 0): a "segment" is a
+// (source, horizontal tap, channel block) unit.  Its A operand is ONE TMA box of
+// (TH+2) x TW pixels; the three vertical taps read that buffer at row offsets
+// 0, TW, 2*TW - whole 8-row swizzle groups, so the shifted descriptors stay
+// canonical - and its B operand is one 3-D box holding the three taps' weight
+// blocks.  L2->SM requests per tile drop from 9*(128+N) to 3*(TW*(TH+2)+3N).
+template <int SWA, int BLOCK_N, bool HALO>
 __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using Cfg = CgCfg<SWA, BLOCK_N>;
     constexpr int KB = Cfg::KB;
@@ -91,7 +102,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     uint8_t* stage_base = smem;
-    uint8_t* stg = smem + stages * Cfg::STAGE_BYTES;  // D staging, 1024-aligned
+    const int a_bytes = HALO ? p.a_stage_bytes : Cfg::A_BYTES;
+    const int stage_bytes = HALO ? p.a_stage_bytes + 3 * Cfg::B_BYTES : Cfg::STAGE_BYTES;
+    uint8_t* stg = smem + stages * stage_bytes;  // D staging, 1024-aligned
     float* scratch = reinterpret_cast<float*>(stg + Cfg::D_BYTES);
     float* acc_sum = reinterpret_cast<float*>(stg + Cfg::D_BYTES + Cfg::SCRATCH_BYTES);
     float* acc_sq = acc_sum + 512;
@@ -152,12 +165,20 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     const CgSeg seg = p.segs[sg];
                     for (int cb = 0; cb < seg.cblocks; ++cb) {
                         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                        uint8_t* a_dst = stage_base + s * Cfg::STAGE_BYTES;
-                        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                        ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
-                                         y0 + seg.dy, n0);
-                        ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                        uint8_t* a_dst = stage_base + s * stage_bytes;
+                        uint8_t* b_dst = a_dst + a_bytes;
+                        if (HALO) {
+                            const uint32_t a_box = uint32_t(p.TW * (p.TH + 2) * SWA);
+                            ptx::mbar_arrive_expect_tx(&full_bar[s], a_box + 3 * Cfg::B_BYTES);
+                            ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                             y0 - 1, n0);
+                            ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                            ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                             y0 + seg.dy, n0);
+                            ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                        }
                         ++kcount;
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
@@ -178,15 +199,27 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                 for (int kb = 0; kb < p.kblocks_total; ++kb) {
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(stage_base + s * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-                    const uint64_t adesc = ptx::make_smem_desc(a_addr, 16, SBO_A, LAYOUT_A);
-                    const uint64_t bdesc = ptx::make_smem_desc(b_addr, 16, SBO_A, LAYOUT_A);
+                    const uint32_t a_addr = ptx::smem_u32(stage_base + s * stage_bytes);
+                    const uint32_t b_addr = a_addr + a_bytes;
+                    if (HALO) {
 #pragma unroll
-                    for (int k = 0; k < KB / 16; ++k) {
-                        // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                         (kb | k) != 0 ? 1u : 0u);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t adesc = ptx::make_smem_desc(a_addr + dy * p.TW * SWA, 16, SBO_A, LAYOUT_A);
+                            const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
+#pragma unroll
+                            for (int k = 0; k < KB / 16; ++k)
+                                ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                 (kb | dy | k) != 0 ? 1u : 0u);
+                        }
+                    } else {
+                        const uint64_t adesc = ptx::make_smem_desc(a_addr, 16, SBO_A, LAYOUT_A);
+                        const uint64_t bdesc = ptx::make_smem_desc(b_addr, 16, SBO_A, LAYOUT_A);
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) {
+                            // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
+                            ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                             (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     ptx::tc_commit(&empty_bar[s]);
                     if (++s == stages) { s = 0; ph ^= 1; }

@@ -47,9 +47,12 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 // mode 2: first layer       dst[co][k], k = tap*Ci + ci<54 = W[co][ci][tap], zero-padded to Kpad
 // mode 3: convT forward     dst[(q*Co + co)][ci]          = W[ci][co][q]      (W is [Ci][Co][2][2])
 // mode 4: convT dgrad       dst[ci][q*Co + co]            = W[ci][co][q]
+// row-halo K order (conv_gemm HALO): k = ((dx*blocks + cb)*3 + dy)*KB + c, channel = cb*KB + c, tap = dy*3 + dx
+// mode 5: conv3x3 forward   dst[co][k]                    = W[co][channel][tap]           (Kpad = KB)
+// mode 6: conv3x3 dgrad     dst[ci][k]                    = W[channel][ci][8 - tap]       (Kpad = KB)
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int mode, int Co, int Ci,
                                    int Kpad) {
-    const int total = (mode == 2) ? Co * Kpad : (mode >= 3 ? 4 * Co * Ci : 9 * Co * Ci);
+    const int total = (mode == 2) ? Co * Kpad : ((mode == 3 || mode == 4) ? 4 * Co * Ci : 9 * Co * Ci);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (mode == 0) {
@@ -64,6 +67,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
                 const int tap = k / Ci, ci = k % Ci;
                 v = w[(co * Ci + ci) * 9 + tap];
             }
+        } else if (mode == 5 || mode == 6) {
+            const int KB = Kpad;
+            const int kin = mode == 5 ? Ci : Co;      // channels on the K side
+            const int row = i / (9 * kin), k = i % (9 * kin);
+            const int blocks = kin / KB;
+            const int c = k % KB, dy = (k / KB) % 3, unit = k / (3 * KB);
+            const int dx = unit / blocks, cb = unit % blocks;
+            const int chan = cb * KB + c, tap = dy * 3 + dx;
+            v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
         } else if (mode == 3) {
             const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
             v = w[(ci * Co + co) * 4 + q];

@@ -101,6 +101,21 @@ static int encode2(CUtensorMap* m, const void* base, int K, int Nrows, int bK, i
     return 0;
 }
 
+// 3-D weight map for the row-halo kernels: (KB, N rows, K blocks); box (KB, bN, 3)
+static int encode3(CUtensorMap* m, const void* base, int KB, int Nrows, int kblocks, int bN, int swizzle_bytes) {
+    cuuint64_t dims[3] = {(cuuint64_t)KB, (cuuint64_t)Nrows, (cuuint64_t)kblocks};
+    cuuint64_t strides[2] = {(cuuint64_t)kblocks * KB * 2, (cuuint64_t)KB * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)bN, 3};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail("cuTensorMapEncodeTiled(3d) failed: %d (KB=%d N=%d kb=%d box=%d sw=%d)", (int)r, KB, Nrows, kblocks,
+                    bN, swizzle_bytes);
+    return 0;
+}
+
 // ------------------------------------------------------------- tile shapes
 struct Tile {
     int TW, TH, TN;
@@ -133,6 +148,7 @@ struct Act {
 struct GemmOp {
     ConvGemmParams p;
     int swa = 128, block_n = 32, grid = 1, smem = 0;
+    bool halo = false;  // row-halo A boxes (3x3 convs); the packed weights use the matching K order
 };
 struct WgradOp {
     WgradParams p;
@@ -240,25 +256,40 @@ static inline int lvl_h(const sdn_ctx* c, int lvl) { return c->H >> (lvl - 1); }
 static inline int lvl_w(const sdn_ctx* c, int lvl) { return c->W >> (lvl - 1); }
 
 // -------------------------------------------------------------- launchers
-template <int SWA, int BN>
+template <int SWA, int BN, bool HALO>
 static int launch_cg_t(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
-    conv_gemm_kernel<SWA, BN><<<op.grid, 192, op.smem, st>>>(op.p);
+    conv_gemm_kernel<SWA, BN, HALO><<<op.grid, 192, op.smem, st>>>(op.p);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    if (op.halo) {
+        if (op.swa == 128) {
+            switch (op.block_n) {
+                case 32: return launch_cg_t<128, 32, true>(c, op, st);
+                case 64: return launch_cg_t<128, 64, true>(c, op, st);
+                case 128: return launch_cg_t<128, 128, true>(c, op, st);
+            }
+        } else if (op.swa == 64) {
+            switch (op.block_n) {
+                case 32: return launch_cg_t<64, 32, true>(c, op, st);
+                case 64: return launch_cg_t<64, 64, true>(c, op, st);
+            }
+        }
+        return fail("no row-halo conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
+    }
     if (op.swa == 128) {
         switch (op.block_n) {
-            case 32: return launch_cg_t<128, 32>(c, op, st);
-            case 64: return launch_cg_t<128, 64>(c, op, st);
-            case 128: return launch_cg_t<128, 128>(c, op, st);
-            case 256: return launch_cg_t<128, 256>(c, op, st);
+            case 32: return launch_cg_t<128, 32, false>(c, op, st);
+            case 64: return launch_cg_t<128, 64, false>(c, op, st);
+            case 128: return launch_cg_t<128, 128, false>(c, op, st);
+            case 256: return launch_cg_t<128, 256, false>(c, op, st);
         }
     } else if (op.swa == 64) {
         switch (op.block_n) {
-            case 32: return launch_cg_t<64, 32>(c, op, st);
-            case 64: return launch_cg_t<64, 64>(c, op, st);
+            case 32: return launch_cg_t<64, 32, false>(c, op, st);
+            case 64: return launch_cg_t<64, 64, false>(c, op, st);
         }
     }
     return fail("no conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
@@ -272,17 +303,26 @@ static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
 }
 static int set_smem_attrs() {
     const int big = 227 * 1024;
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define SDN_SMEM_ATTR(...) CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
+    SDN_SMEM_ATTR(128, 32, false); SDN_SMEM_ATTR(128, 64, false); SDN_SMEM_ATTR(128, 128, false);
+    SDN_SMEM_ATTR(128, 256, false); SDN_SMEM_ATTR(64, 32, false); SDN_SMEM_ATTR(64, 64, false);
+    SDN_SMEM_ATTR(128, 32, true); SDN_SMEM_ATTR(128, 64, true); SDN_SMEM_ATTR(128, 128, true);
+    SDN_SMEM_ATTR(64, 32, true); SDN_SMEM_ATTR(64, 64, true);
+#undef SDN_SMEM_ATTR
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
 }
 
+static int cg_smem_halo(int swa, int bn, int stages, int a_stage_bytes) {
+    if (swa == 128) {
+        if (bn == 32) return CgCfg<128, 32>::smem_bytes_halo(stages, a_stage_bytes);
+        if (bn == 64) return CgCfg<128, 64>::smem_bytes_halo(stages, a_stage_bytes);
+        return CgCfg<128, 128>::smem_bytes_halo(stages, a_stage_bytes);
+    }
+    if (bn == 32) return CgCfg<64, 32>::smem_bytes_halo(stages, a_stage_bytes);
+    return CgCfg<64, 64>::smem_bytes_halo(stages, a_stage_bytes);
+}
 static int cg_smem(int swa, int bn, int stages) {
     if (swa == 128) {
         if (bn == 32) return CgCfg<128, 32>::smem_bytes(stages);
@@ -326,10 +366,17 @@ static SrcView quad_view(const Act& u, int q) {
 struct SegSpec {
     int view, dx, dy;
 };
+static int g_halo_max_n = -1;  // SDN_HALO_MAXN: largest BLOCK_N that uses the row-halo kernel (0 disables)
+
 static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
-                      const std::vector<SegSpec>& segs, const bf16* bmat, int n_total,
+                      const std::vector<SegSpec>& segs_in, const bf16* bmat, int n_total,
                       const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
-                      float* stats_partials) {
+                      float* stats_partials, bool conv3x3 = false) {
+    if (g_halo_max_n < 0) {
+        const char* e = getenv("SDN_HALO_MAXN");
+        g_halo_max_n = e ? atoi(e) : 128;
+    }
+    std::vector<SegSpec> segs = segs_in;
     if (aviews.empty() || aviews.size() > 4 || dviews.empty() || dviews.size() > 4 || segs.size() > CG_MAX_SEGS)
         return fail("build_gemm: bad view/segment counts");
     memset(&op.p, 0, sizeof op.p);
@@ -345,7 +392,22 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     if (n_per_dmap % bn != 0) return fail("build_gemm: N %d not divisible by BLOCK_N %d", n_per_dmap, bn);
     op.block_n = bn;
     const int W = dviews[0].W, H = dviews[0].H;
-    const Tile t = choose_tile(W, H, B, 128);
+    op.halo = conv3x3 && bn <= g_halo_max_n;
+    Tile t = choose_tile(W, H, B, 128);
+    if (op.halo) {
+        // one image per box and TW % 8 == 0 so the vertical-tap row shifts are whole swizzle groups
+        double best = 1e300;
+        for (int TW = 8; TW <= 32; TW *= 2) {
+            const int TH = 128 / TW;
+            const double padded = double((W + TW - 1) / TW * TW) * double((H + TH - 1) / TH * TH);
+            const double cost = padded * double(TH + 2) / double(TH);
+            if (cost < best) { best = cost; t = Tile{TW, TH, 1}; }
+        }
+        // units: (horizontal tap, source); each contributes all of its channel blocks, 3 vertical taps each
+        segs.clear();
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int sv = 0; sv < (int)aviews.size(); ++sv) segs.push_back({sv, dx, 0});
+    }
     ConvGemmParams& p = op.p;
     p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
     p.tiles_x = (W + t.TW - 1) / t.TW;
@@ -354,8 +416,10 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
-        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, t.TW, t.TH, t.TN, op.swa));
+        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, t.TW, op.halo ? t.TH + 2 : t.TH,
+                       t.TN, op.swa));
     }
+    p.a_stage_bytes = (t.TW * (t.TH + 2) * op.swa + 1023) & ~1023;
     for (size_t i = aviews.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
     int kblocks = 0;
     p.nsegs = (int)segs.size();
@@ -369,7 +433,8 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         kblocks += g.cblocks;
     }
     p.kblocks_total = kblocks;
-    SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
+    if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * 3, bn, op.swa));
+    else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
     const int swd = bn >= 64 ? 128 : 64;
     const int dch = swd / 2;
     for (size_t i = 0; i < dviews.size(); ++i) {
@@ -385,16 +450,21 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.stats_partials = stats_partials;
     if ((flags & CG_STATS) && n_total > 512) return fail("build_gemm: stats need n_total <= 512");
     int stages = 8;
-    while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
+    if (op.halo) {
+        while (stages > 2 && cg_smem_halo(op.swa, bn, stages, p.a_stage_bytes) > 220 * 1024) --stages;
+        op.smem = cg_smem_halo(op.swa, bn, stages, p.a_stage_bytes);
+    } else {
+        while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
+        op.smem = cg_smem(op.swa, bn, stages);
+    }
     p.stages = stages;
-    op.smem = cg_smem(op.swa, bn, stages);
     const int num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
     op.grid = std::max(1, std::min(num_tiles, c->num_sms));
     return 0;
 }
 
 // Weight-gradient op.  avariants: dY views (1, or the 4 quadrants for convT);
-// bsrc: 1 or 2 X sources; taps 9 or 1.
+// bsrc: 1 or 2 X sources; taps 9 (row-halo units, see wgrad_gemm.cuh) or 1.
 static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView>& avariants, int cout,
                        const std::vector<SrcView>& bsrc, int taps, float* out, int k_rows_valid) {
     memset(&op.p, 0, sizeof op.p);
@@ -409,7 +479,21 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     op.swb = all64 ? 128 : 64;
     const int CA = op.swb / 2;
     const int W = avariants[0].W, H = avariants[0].H;
-    const Tile t = choose_tile(W, H, B, 64);
+    p.halo = taps == 9 ? 1 : 0;
+    Tile t;
+    if (p.halo) {
+        // one image per box, TW a multiple of 8 (row shifts must be whole swizzle groups)
+        double best = 1e300;
+        t = Tile{8, 8, 1};
+        for (int TW = 8; TW <= 64; TW *= 2) {
+            const int TH = 64 / TW;
+            const double padded = double((W + TW - 1) / TW * TW) * double((H + TH - 1) / TH * TH);
+            const double cost = padded * double(TH + 2) / double(TH);
+            if (cost < best) { best = cost; t = Tile{TW, TH, 1}; }
+        }
+    } else {
+        t = choose_tile(W, H, B, 64);
+    }
     p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
     p.kpix = 64;
     p.tiles_x = (W + t.TW - 1) / t.TW;
@@ -423,31 +507,41 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
         SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, 64, t.TW, t.TH, t.TN, 128));
     }
     for (size_t i = avariants.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    const int b_rows = p.halo ? (t.TH + 2) * t.TW : p.kpix;
     for (size_t i = 0; i < bsrc.size(); ++i) {
         const SrcView& v = bsrc[i];
-        SDN_OK(encode4(&p.b_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, CA, t.TW, t.TH, t.TN, op.swb));
+        SDN_OK(encode4(&p.b_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, CA, t.TW, p.halo ? t.TH + 2 : t.TH,
+                       t.TN, op.swb));
     }
     if (bsrc.size() == 1) p.b_maps[1] = p.b_maps[0];
-    p.taps = taps;
     p.atoms_per_tap = cin_tot / CA;
     p.atoms_src0 = bsrc[0].C / CA;
-    const int total_atoms = taps * p.atoms_per_tap;
-    p.G = std::min(total_atoms, 256 / CA);
-    p.n_groups = (total_atoms + p.G - 1) / p.G;
+    const int ndy = p.halo ? 3 : 1;
+    p.total_units = (p.halo ? 3 : 1) * p.atoms_per_tap;
+    const int a_bytes = p.a_atoms * p.kpix * 128;
+    const int b_tile_bytes = (b_rows * op.swb + 1023) & ~1023;
+    int umax = std::min(p.total_units, 512 / (ndy * CA));
+    while (umax > 1 && 3 * (a_bytes + umax * b_tile_bytes) + 2048 > 200 * 1024) --umax;  // keep >= 3 stages
+    p.unit_groups = (p.total_units + umax - 1) / umax;
+    p.U = (p.total_units + p.unit_groups - 1) / p.unit_groups;
+    p.unit_groups = (p.total_units + p.U - 1) / p.U;
+    int cols = 32;
+    while (cols < p.U * ndy * CA) cols *= 2;
+    p.tmem_cols = cols;
     p.cout = cout;
     p.cin_tot = cin_tot;
     p.k_rows_valid = k_rows_valid;
     p.out = out;
-    const int stage_bytes = p.a_atoms * p.kpix * 128 + p.G * p.kpix * op.swb;
+    const int stage_bytes = a_bytes + p.U * b_tile_bytes;
     int stages = 8;
     while (stages > 2 && stages * stage_bytes + 2048 > 200 * 1024) --stages;
     p.stages = stages;
     op.smem = stages * stage_bytes + 2048;
     const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int ctas_per_split = p.n_groups * p.m_tiles * p.a_variants;
+    const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
     int split = (2 * c->num_sms + ctas_per_split - 1) / ctas_per_split;
     split = std::max(1, std::min(split, ptiles));
-    op.grid = dim3(split, p.n_groups, p.m_tiles * p.a_variants);
+    op.grid = dim3(split, p.unit_groups, p.m_tiles * p.a_variants);
     return 0;
 }
 
@@ -586,7 +680,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
                 for (int s = 0; s < L.nsrc; ++s) segs.push_back({s, k3x3[tap].dx, k3x3[tap].dy});
         }
         SDN_OK(build_gemm(c, L.fprop, B, av, segs, L.wf, L.cout, {full_view(L.y)}, L.cout, nullptr, CG_STATS,
-                          c->stats_partials));
+                          c->stats_partials, !L.first));
         // ---- data gradient: conv3x3 of dy with flipped / transposed weights
         if (L.has_dgrad) {
             std::vector<SegSpec> dsegs(k3x3, k3x3 + 9);
@@ -603,7 +697,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
             } else {
                 dv.push_back(full_view(c->conv[i - 1].gp));
             }
-            SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr));
+            SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr, true));
         }
         // ---- weight gradient
         std::vector<SrcView> bs;
@@ -644,10 +738,12 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
             ++c->launches;
         } else {
             const int n = 9 * L.cin * L.cout;
-            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wf, 0, L.cout, L.cin, 0);
+            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wf, L.fprop.halo ? 5 : 0, L.cout, L.cin,
+                                                                   L.fprop.swa / 2);
             ++c->launches;
             if (training) {
-                pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wd, 1, L.cout, L.cin, 0);
+                pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wd, L.dgrad.halo ? 6 : 1, L.cout, L.cin,
+                                                                       L.dgrad.swa / 2);
                 ++c->launches;
             }
         }

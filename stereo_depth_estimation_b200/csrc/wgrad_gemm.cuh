@@ -10,31 +10,42 @@
 // (64 channels, TW, TH, TN) lands in shared memory as [pixels][128 B] with the
 // 128-byte swizzle, which is exactly the canonical MN-major SW128 atom column
 // (8-row groups 1024 B apart = SBO, channel atoms LBO apart).
+//
 //   A (M side) = dY: one or two 64-channel atoms -> M = 128 (with one atom the
 //                second half aliases the first via LBO = 0 and is ignored).
-//   B (N side) = up to G atoms, each its own TMA box: a (filter tap, channel
-//                block) of X shifted by the tap; N = atoms * CA <= 256.
-// Each CTA owns one (co tile, atom group) and a split of the pixel tiles; fp32
-// partial sums are merged with red.global.add into a [k][co] workspace.
+//   B (N side) = "units".  For a 3x3 conv a unit is (horizontal tap dx, channel
+//                atom): ONE TMA box of (TH+2) x TW pixels whose three vertical taps
+//                are the same buffer read at row offsets 0, TW, 2*TW.  TW is a
+//                multiple of 8, so those offsets are whole 8-row swizzle groups
+//                and the shifted views stay canonical: the three taps are three
+//                N-atoms LBO = TW rows apart and cost ONE load instead of three.
+//                For 1x1 / ConvTranspose2d a unit is a plain channel atom.
+//   One CTA owns (co tile) x (up to U units) with all of their accumulators in
+//   TMEM (<= 512 columns), so dY is fetched once per pixel tile for all taps.
+// The kernel is bound by L2->SM request throughput, not by the tensor pipe; the
+// layout above cuts the requests per pixel ~4x against one box per tap.
+// Split-K over pixel tiles; fp32 partials merged with red.global.add.
 #pragma once
 #include "ptx.cuh"
 
 namespace sdn {
 
 struct alignas(64) WgradParams {
-    CUtensorMap a_maps[4];  // dY variants (convT: the 4 output quadrants)
-    CUtensorMap b_maps[2];  // X sources (skip-concat: two tensors)
+    CUtensorMap a_maps[4];  // dY variants (convT: the 4 output quadrants), box (64, TW, TH, TN)
+    CUtensorMap b_maps[2];  // X sources, box (CA, TW, TH + 2*halo, TN)
     int a_atoms;            // 1 or 2 64-channel atoms on the M side
     int a_variants;         // 1, or 4 for ConvTranspose2d
     int m_tiles;            // ceil(Cout / 128)
-    int G;                  // B atoms per CTA
-    int taps;               // 9 (3x3) or 1
+    int halo;               // 1: 3x3 conv (ndy = 3 row-shifted taps per unit), 0: single tap
+    int U;                  // units per CTA
+    int total_units;        // halo: 3 * atoms_per_tap, else atoms_per_tap
     int atoms_per_tap;      // Cin_total / CA
     int atoms_src0;         // atoms that come from b_maps[0]
-    int n_groups;           // ceil(taps * atoms_per_tap / G)
+    int unit_groups;        // ceil(total_units / U)
     int tiles_x, tiles_y, tiles_n, TW, TH, TN;
-    int kpix;               // TW*TH*TN (64 or 128)
+    int kpix;               // TW*TH*TN
     int stages;
+    int tmem_cols;          // power of two >= U * ndy * CA
     int cout;               // valid output channels (row length of the workspace)
     int cin_tot;
     int k_rows_valid;       // rows of the workspace that exist
@@ -49,9 +60,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
+    const int ndy = p.halo ? 3 : 1;
     const int a_tile_bytes = p.kpix * 128;
-    const int b_tile_bytes = p.kpix * SWB;
-    const int stage_bytes = p.a_atoms * a_tile_bytes + p.G * b_tile_bytes;
+    const int b_rows = p.halo ? (p.TH + 2) * p.TW : p.kpix;
+    const int b_tile_bytes = ((b_rows * SWB) + 1023) & ~1023;
+    const int stage_bytes = p.a_atoms * a_tile_bytes + p.U * b_tile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + 8;
@@ -63,11 +76,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
 
     const int variant = blockIdx.z / p.m_tiles;
     const int m_tile = blockIdx.z % p.m_tiles;
-    const int group = blockIdx.y;
-    const int total_atoms = p.taps * p.atoms_per_tap;
-    const int atom0 = group * p.G;
-    const int natoms = min(p.G, total_atoms - atom0);
-    const int N = natoms * CA;
+    const int unit0 = blockIdx.y * p.U;
+    const int nunits = min(p.U, p.total_units - unit0);
     const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
 
     if (threadIdx.x == 0) {
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr_smem, 256);
+        ptx::tmem_alloc(tmem_ptr_smem, p.tmem_cols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             ptx::prefetch_tmap(&p.b_maps[1]);
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx_bytes = p.a_atoms * a_tile_bytes + natoms * b_tile_bytes;
+            const uint32_t tx_bytes = p.a_atoms * a_tile_bytes + nunits * (b_rows * SWB);
             for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
                 const int tx = t % p.tiles_x;
                 const int ty = (t / p.tiles_x) % p.tiles_y;
@@ -110,15 +120,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 for (int i = 0; i < p.a_atoms; ++i)
                     ptx::tma_load_4d(a_dst + i * a_tile_bytes, &p.a_maps[variant], &full_bar[s],
                                      m_tile * 128 + i * 64, x0, y0, n0);
-                for (int g = 0; g < natoms; ++g) {
-                    const int u = atom0 + g;
-                    const int tap = u / p.atoms_per_tap;
-                    const int ca = u % p.atoms_per_tap;
-                    int dx = 0, dy = 0;
-                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                for (int g = 0; g < nunits; ++g) {
+                    const int u = unit0 + g;
+                    const int dxi = p.halo ? u / p.atoms_per_tap : 1;
+                    const int ca = p.halo ? u % p.atoms_per_tap : u;
                     const int src = ca < p.atoms_src0 ? 0 : 1;
                     const int c0 = (src == 0 ? ca : ca - p.atoms_src0) * CA;
-                    ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[src], &full_bar[s], c0, x0 + dx, y0 + dy, n0);
+                    ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[src], &full_bar[s], c0, x0 + dxi - 1,
+                                     y0 - p.halo, n0);
                 }
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
@@ -127,8 +136,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t idesc = ptx::make_idesc_bf16(128, N, 1, 1);
+            const uint32_t idesc = ptx::make_idesc_bf16(128, ndy * CA, 1, 1);
             const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
+            const uint32_t b_lbo = uint32_t(p.TW * SWB);  // one image row of the halo box = one vertical tap
             for (int it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
@@ -137,9 +147,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 for (int k = 0; k < p.kpix / 16; ++k) {
                     // 16 pixels = two 8-row groups: advance by 16 rows of the atom column
                     const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 16 * 128, a_lbo, 1024, 2u);
-                    const uint64_t bdesc =
-                        ptx::make_smem_desc(b_addr + k * 16 * SWB, uint32_t(b_tile_bytes), 8 * SWB, LAYOUT_B);
-                    ptx::tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+                    for (int g = 0; g < nunits; ++g) {
+                        const uint64_t bdesc = ptx::make_smem_desc(b_addr + g * b_tile_bytes + k * 16 * SWB, b_lbo,
+                                                                   8 * SWB, LAYOUT_B);
+                        ptx::tc_mma_bf16(tmem_base + g * ndy * CA, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
                 }
                 ptx::tc_commit(&empty_bar[s]);
                 if (++s == stages) { s = 0; ph ^= 1; }
@@ -154,18 +166,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         if (my_tiles > 0) {
             ptx::mbar_wait(tfull_bar, 0);
             ptx::tc_fence_after();
-            float* out = p.out + size_t(variant) * p.taps * p.cin_tot * p.cout;
+            const int taps = p.halo ? 9 : 1;
+            float* out = p.out + size_t(variant) * taps * p.cin_tot * p.cout;
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
-            for (int ch = 0; ch < N / 32; ++ch) {
+            const int ncols = nunits * ndy * CA;
+            for (int ch = 0; ch < ncols / 32; ++ch) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(taddr + ch * 32, v);
                 ptx::tmem_ld_wait();
                 if (row_ok) {
                     const int cn0 = ch * 32;
-                    const int g = cn0 / CA;
-                    const int u = atom0 + g;
-                    const int tap = u / p.atoms_per_tap;
-                    const int ca = u % p.atoms_per_tap;
+                    const int g = cn0 / (ndy * CA);
+                    const int dyi = (cn0 % (ndy * CA)) / CA;
+                    const int u = unit0 + g;
+                    const int dxi = p.halo ? u / p.atoms_per_tap : 0;
+                    const int ca = p.halo ? u % p.atoms_per_tap : u;
+                    const int tap = p.halo ? dyi * 3 + dxi : 0;
                     const int krow0 = tap * p.cin_tot + ca * CA + (cn0 % CA);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 256);
+        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 

@@ -363,32 +363,34 @@ def test_fused_step_skips_batch_without_valid_pixels(dev):
 
 
 def test_run_epoch_tracks_oracle_curve(dev):
-    """A short synthetic training curve: fused CUDA steps vs the fp32 oracle, same data."""
+    """A few-hundred-step synthetic training curve: fused CUDA steps (bf16 tensor cores)
+    vs the fp32 oracle on the same data and the same AdamW settings.  The two
+    trajectories are chaotic relative to each other at the 1e-3 level, so the curve is
+    compared per 20-step segment with an 8 % band."""
     from stereo_depth_estimation_b200.step import run_epoch
 
-    b, h, w, steps = 4, 64, 96, 12
-    batches = [make_batch(dev, b, h, w, seed=300 + i) for i in range(steps)]
+    b, h, w, steps, seg = 4, 64, 96, 240, 20
+    batches = [make_batch(dev, b, h, w, seed=300 + i) for i in range(24)]   # cycled
     model, sd = fresh_model(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
-    logged = []
-    ours = []
+    logged, ours, ref = [], [], []
     osd = {k: v.clone() for k, v in sd.items()}
     oopt = so.AdamWState()
-    ref = []
     gs = 0
-    for i in range(0, steps, 4):
-        m, gs = run_epoch(model, batches[i:i + 4], dev, optimizer=opt, global_step=gs, log_every_batches=2,
+    for i in range(0, steps, seg):
+        chunk = [batches[(i + j) % len(batches)] for j in range(seg)]
+        m, gs = run_epoch(model, chunk, dev, optimizer=opt, global_step=gs, log_every_batches=10,
                           log_metrics=lambda d, step: logged.append((step, d)))
         ours.append(m["loss"])
-        ref.append(so.run_epoch(osd, batches[i:i + 4], oopt)["loss"])
-    assert gs == steps and len(logged) == steps // 2
+        ref.append(so.run_epoch(osd, chunk, oopt)["loss"])
+    assert gs == steps and len(logged) == steps // 10
     assert set(logged[0][1]) == {"train_loss_step", "train_nll_step", "train_mae_step", "train_rmse_step", "train_sigma_step"}
     for a_, r_ in zip(ours, ref):
-        assert a_ == pytest.approx(r_, rel=3e-2)
-    assert ours[-1] < ours[0]
+        assert a_ == pytest.approx(r_, rel=8e-2), (ours, ref)
+    assert ours[-1] < 0.8 * ours[0] and ref[-1] < 0.8 * ref[0]
     val, _ = run_epoch(model, batches[:2], dev, optimizer=None)
     oval = so.run_epoch(osd, batches[:2], None)
-    assert val["mae"] == pytest.approx(oval["mae"], rel=5e-2)
+    assert val["mae"] == pytest.approx(oval["mae"], rel=1.5e-1)
 
 
 def test_checkpoint_round_trip_and_compat(dev):
