@@ -211,7 +211,7 @@ def run_b200(args):
 
     def one_step(src):
         nonlocal out
-        out = pre(src[0], src[1], src[2], aug=sampler.sample_batch(b_local), out=out, count_out=count)
+        out = pre(src[0], src[1], src[2], aug=sampler.sample_packed(b_local), out=out, count_out=count)
         return step.train_step(out, valid_count=count)
 
     def barrier():

@@ -106,6 +106,7 @@ int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask
  * single-threaded DataLoader worker runs on small / 3-channel images; results
  * differ by <= 1 ulp, indices and weights are identical); 0 = canonical form. */
 #define SDN_RESIZE_FOURTERM 1u
+#define SDN_PREPROCESS_DIRECT 2u /* flags: force the un-staged kernel (tests compare both) */
 int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
                    unsigned long long* valid_count, unsigned flags, void* stream);

@@ -95,18 +95,35 @@ __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict_
 // ------------------------------------------------------- first-layer im2col
 // x fp32 NCHW [B,Cin,H,W] (the reference sample layout, dataset.py:305-311) ->
 // bf16 [B,H,W,64] with k = (dy*3+dx)*Cin + c, zero padding at the border and
-// zeros for k >= 9*Cin.  One thread = 8 consecutive k of one pixel (16-byte store).
-__global__ void im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H,
-                                    int W) {
-    const long long total = (long long)B * H * W * 8;
+// zeros for k >= 9*Cin.  One block = one output row segment of IM2COL_PX pixels:
+// the 3 x Cin input row segments are staged in shared memory with coalesced
+// loads, then every thread emits 16-byte chunks (8 consecutive k of one pixel),
+// so 8 consecutive threads write one pixel's 128 contiguous bytes.
+constexpr int IM2COL_PX = 128;
+constexpr int IM2COL_MAXC = 8;
+
+__global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
+                                                           int Cin, int H, int W) {
+    __shared__ float tile[IM2COL_MAXC * 3][IM2COL_PX + 2];
+    const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
+    const int xb = blockIdx.x % xblocks;
+    const int yh = (blockIdx.x / xblocks) % H;
+    const int n = blockIdx.x / (xblocks * H);
+    const int x0 = xb * IM2COL_PX;
     const int K = 9 * Cin;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int g = int(i & 7);
-        const long long pix = i >> 3;
-        const int xw = int(pix % W);
-        const int yh = int((pix / W) % H);
-        const int n = int(pix / ((long long)W * H));
+    for (int i = threadIdx.x; i < Cin * 3 * (IM2COL_PX + 2); i += blockDim.x) {
+        const int col = i % (IM2COL_PX + 2);
+        const int row = i / (IM2COL_PX + 2);  // c * 3 + dy
+        const int c = row / 3, dy = row % 3;
+        const int yy = yh + dy - 1, xx = x0 + col - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * Cin + c) * H + yy) * W + xx);
+        tile[row][col] = v;
+    }
+    __syncthreads();
+    const int npx = min(IM2COL_PX, W - x0);
+    for (int i = threadIdx.x; i < npx * 8; i += blockDim.x) {
+        const int g = i & 7, px = i >> 3;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -114,11 +131,11 @@ __global__ void im2col_first_kernel(const float* __restrict__ x, bf16* __restric
             float v = 0.f;
             if (k < K) {
                 const int tap = k / Cin, c = k % Cin;
-                const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((long long)n * Cin + c) * H + yy) * W + xx);
+                v = tile[c * 3 + tap / 3][px + tap % 3];
             }
             f[j] = v;
         }
+        const size_t pix = ((size_t)n * H + yh) * W + x0 + px;
         *reinterpret_cast<uint4*>(out + pix * 64 + g * 8) = pack8(f);
     }
 }

@@ -799,7 +799,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     {
         const double px = (double)B * H * W;
         ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + 64 * 2));
-        im2col_first_kernel<<<ew_grid(c, (long long)B * H * W * 8, 256), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
+        im2col_first_kernel<<<B * H * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
@@ -1131,8 +1131,31 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
     const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
     // 3 uint8 sources read + fp32 input/target + u8 mask written per sample
-    ProfScope ps(c, st, "preprocess", 0, 0.0, (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
-    if (flags & SDN_RESIZE_FOURTERM)
+    // decode+resize moves the SURVEY 8(d) bytes; the augmentation passes re-read / re-write the fp32 views
+    ProfScope* ps = new ProfScope(c, st, "pre_decode_resize", 0, 0.0,
+                                  (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
+    // shared-memory staged kernel when the source rows are 16-byte aligned and the footprint fits
+    const int max_rows = (int)std::ceil((double)PRE_ROWS * Hs / H) + 3;
+    const int row_bytes = (((int)std::ceil(128.0 * Ws / W) + 3) * 3 + 47) & ~15;
+    const size_t pre_smem = (size_t)3 * max_rows * row_bytes;
+    const bool aligned = ((Ws * 3) % 16 == 0) && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)disparity) % 16 == 0);
+    const bool staged = aligned && pre_smem <= 200 * 1024 && !(flags & SDN_PREPROCESS_DIRECT);
+    if (staged) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        if (flags & SDN_RESIZE_FOURTERM)
+            decode_resize_smem_kernel<true><<<dim3(parts, B), 256, pre_smem, st>>>(
+                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
+                aug ? c->gray_part : nullptr, parts, max_rows, row_bytes);
+        else
+            decode_resize_smem_kernel<false><<<dim3(parts, B), 256, pre_smem, st>>>(
+                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
+                aug ? c->gray_part : nullptr, parts, max_rows, row_bytes);
+    } else if (flags & SDN_RESIZE_FOURTERM)
         decode_resize_kernel<true><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
                                                                    target, mask, valid_count, aug,
                                                                    aug ? c->gray_part : nullptr, parts);
@@ -1141,7 +1164,9 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
                                                                     target, mask, valid_count, aug,
                                                                     aug ? c->gray_part : nullptr, parts);
     ++c->launches;
+    delete ps;
     if (aug != nullptr) {
+        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
         augment_point_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(input, B, H, W, aug, c->gray_part, parts,
                                                                               c->blur_tmp);
         ++c->launches;

@@ -180,6 +180,132 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
     }
 }
 
+// Shared-memory staged variant of decode_resize_kernel (same arithmetic, bit-exact):
+// the block first copies the source byte ranges it needs (all three images) into
+// shared memory with 128-bit coalesced loads, then computes from there.  Needs 16-byte
+// aligned image rows (Ws*3 % 16 == 0 and 16-byte aligned bases) - the host falls back
+// to the direct kernel otherwise.  256 threads: 128 output columns x PRE_ROWS rows.
+template <bool FOURTERM>
+__global__ void __launch_bounds__(256) decode_resize_smem_kernel(
+    const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, const uint8_t* __restrict__ D, int B, int Hs, int Ws,
+    int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
+    unsigned long long* __restrict__ valid_count, const AugParams* __restrict__ aug, float* __restrict__ gray_part,
+    int parts_per_view, int max_rows, int row_bytes) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int n = blockIdx.y;
+    const int xblocks = (W + 127) / 128;
+    const int xb = blockIdx.x % xblocks;
+    const int yb = blockIdx.x / xblocks;
+    const float sy = (float)Hs / (float)H;
+    const float sx = (float)Ws / (float)W;
+    const float wscale = (float)((double)W / (double)Ws);
+    const size_t src_img = (size_t)Hs * Ws * 3;
+    const uint8_t* srcs[3] = {L + (size_t)n * src_img, R + (size_t)n * src_img, D + (size_t)n * src_img};
+    const size_t plane = (size_t)H * W;
+
+    // source footprint of this block
+    const int ox0 = xb * 128, ox1 = min(ox0 + 127, W - 1);
+    const int oy0 = yb * PRE_ROWS, oy1 = min(oy0 + PRE_ROWS - 1, H - 1);
+    int a0, a1, b0, b1;
+    float t0, t1;
+    bilinear_src(sx, ox0, Ws, W, a0, a1, t0, t1);
+    bilinear_src(sx, ox1, Ws, W, b0, b1, t0, t1);
+    const int col_first = a0, col_last = b1;
+    bilinear_src(sy, oy0, Hs, H, a0, a1, t0, t1);
+    bilinear_src(sy, oy1, Hs, H, b0, b1, t0, t1);
+    const int row_first = a0, row_last = b1;
+    const int nrows = row_last - row_first + 1;
+    const int byte0 = (col_first * 3) & ~15;                       // 16-byte aligned inside the row
+    const int byte1 = min(((col_last + 1) * 3 + 15) & ~15, Ws * 3);
+    const int chunks = (byte1 - byte0) >> 4;
+    for (int i = threadIdx.x; i < 3 * nrows * chunks; i += blockDim.x) {
+        const int ck = i % chunks;
+        const int rr = (i / chunks) % nrows;
+        const int im = i / (chunks * nrows);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(srcs[im] + (size_t)(row_first + rr) * Ws * 3 + byte0) + ck);
+        *reinterpret_cast<uint4*>(sm + ((size_t)(im * max_rows + rr) * row_bytes) + (ck << 4)) = v;
+    }
+    __syncthreads();
+
+    const int x = ox0 + (threadIdx.x & 127);
+    float gsumL = 0.f, gsumR = 0.f;
+    unsigned int cnt = 0;
+    float fbL = 1.f, fbR = 1.f;
+    if (aug != nullptr) { fbL = aug[2 * n].brightness; fbR = aug[2 * n + 1].brightness; }
+    if (x < W) {
+        int x0, x1;
+        float w0, w1;
+        bilinear_src(sx, x, Ws, W, x0, x1, w0, w1);
+        const int c0 = x0 * 3 - byte0, c1 = x1 * 3 - byte0;
+        for (int yy = (threadIdx.x >> 7); yy < PRE_ROWS; yy += 2) {
+            const int y = oy0 + yy;
+            if (y >= H) break;
+            int y0, y1;
+            float h0, h1;
+            bilinear_src(sy, y, Hs, H, y0, y1, h0, h1);
+            const size_t opix = (size_t)y * W + x;
+            float rgb[2][3];
+#pragma unroll
+            for (int im = 0; im < 2; ++im) {
+                const uint8_t* r0 = sm + (size_t)(im * max_rows + (y0 - row_first)) * row_bytes;
+                const uint8_t* r1 = sm + (size_t)(im * max_rows + (y1 - row_first)) * row_bytes;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float a = __fdiv_rn((float)r0[c0 + c], 255.f);
+                    const float b = __fdiv_rn((float)r0[c1 + c], 255.f);
+                    const float cc = __fdiv_rn((float)r1[c0 + c], 255.f);
+                    const float e = __fdiv_rn((float)r1[c1 + c], 255.f);
+                    rgb[im][c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
+                    input[((size_t)n * 6 + im * 3 + c) * plane + opix] = rgb[im][c];
+                }
+            }
+            const uint8_t* d0 = sm + (size_t)(2 * max_rows + (y0 - row_first)) * row_bytes;
+            const uint8_t* d1 = sm + (size_t)(2 * max_rows + (y1 - row_first)) * row_bytes;
+            const uint8_t* taps[4] = {d0 + c0, d0 + c1, d1 + c0, d1 + c1};
+            float dv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float r = (float)taps[k][0], g = (float)taps[k][1], b = (float)taps[k][2];
+                const float s = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(r, 255.f), 255.f), __fmul_rn(g, 255.f)), b);
+                dv[k] = __fdiv_rn(s, 1000.f);
+            }
+            const float t = __fmul_rn(bilerp<FOURTERM>(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
+            target[(size_t)n * plane + opix] = t;
+            const bool valid = t > 0.f;
+            mask[(size_t)n * plane + opix] = valid ? 1 : 0;
+            cnt += (valid && isfinite(t)) ? 1u : 0u;
+            if (aug != nullptr) {
+                gsumL += gray_of(blend(rgb[0][0], 0.f, fbL, 1.f - fbL), blend(rgb[0][1], 0.f, fbL, 1.f - fbL),
+                                 blend(rgb[0][2], 0.f, fbL, 1.f - fbL));
+                gsumR += gray_of(blend(rgb[1][0], 0.f, fbR, 1.f - fbR), blend(rgb[1][1], 0.f, fbR, 1.f - fbR),
+                                 blend(rgb[1][2], 0.f, fbR, 1.f - fbR));
+            }
+        }
+    }
+    __shared__ float redL[8], redR[8];
+    __shared__ unsigned int redC[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        gsumL += __shfl_xor_sync(0xffffffffu, gsumL, o);
+        gsumR += __shfl_xor_sync(0xffffffffu, gsumR, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { redL[threadIdx.x >> 5] = gsumL; redR[threadIdx.x >> 5] = gsumR; redC[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (gray_part != nullptr) {
+            float a = 0.f, b = 0.f;
+            for (int w8 = 0; w8 < 8; ++w8) { a += redL[w8]; b += redR[w8]; }
+            gray_part[(size_t)(2 * n) * parts_per_view + blockIdx.x] = a;
+            gray_part[(size_t)(2 * n + 1) * parts_per_view + blockIdx.x] = b;
+        }
+        if (valid_count != nullptr) {
+            unsigned int c = 0;
+            for (int w8 = 0; w8 < 8; ++w8) c += redC[w8];
+            if (c) atomicAdd(valid_count, (unsigned long long)c);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- Philox RNG
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&out)[4]) {

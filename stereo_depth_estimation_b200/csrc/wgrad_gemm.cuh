@@ -139,19 +139,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             const uint32_t idesc = ptx::make_idesc_bf16(128, ndy * CA, 1, 1);
             const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
             const uint32_t b_lbo = uint32_t(p.TW * SWB);  // one image row of the halo box = one vertical tap
+            // descriptors of stage 0; later stages / k-steps / units only add to the 14-bit address field
+            const uint32_t smem0 = ptx::smem_u32(smem);
+            const uint64_t adesc0 = ptx::make_smem_desc(smem0, a_lbo, 1024, 2u);
+            const uint64_t bdesc0 = ptx::make_smem_desc(smem0 + p.a_atoms * a_tile_bytes, b_lbo, 8 * SWB, LAYOUT_B);
+            const uint32_t b_unit16 = uint32_t(b_tile_bytes) >> 4;
+            const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
+            const uint32_t ncol = uint32_t(ndy * CA);
             for (int it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
-                const uint32_t b_addr = a_addr + p.a_atoms * a_tile_bytes;
-                for (int k = 0; k < p.kpix / 16; ++k) {
-                    // 16 pixels = two 8-row groups: advance by 16 rows of the atom column
-                    const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 16 * 128, a_lbo, 1024, 2u);
-                    for (int g = 0; g < nunits; ++g) {
-                        const uint64_t bdesc = ptx::make_smem_desc(b_addr + g * b_tile_bytes + k * 16 * SWB, b_lbo,
-                                                                   8 * SWB, LAYOUT_B);
-                        ptx::tc_mma_bf16(tmem_base + g * ndy * CA, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-                    }
+                const uint64_t sa = adesc0 + uint64_t(s * stage16);
+                const uint64_t sb = bdesc0 + uint64_t(s * stage16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
+                    const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
+                    const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
+                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                    for (int g = 0; g < nunits; ++g)
+                        ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
                 }
                 ptx::tc_commit(&empty_bar[s]);
                 if (++s == stages) { s = 0; ph ^= 1; }

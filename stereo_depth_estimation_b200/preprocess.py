@@ -83,6 +83,36 @@ class AugmentSampler:
         """2*batch views in (left, right) order per sample, like dataset.py:302-304."""
         return [self.sample_view() for _ in range(2 * batch)]
 
+    def sample_packed(self, batch: int) -> torch.Tensor:
+        """The same distributions drawn for a whole batch at once (numpy, vectorised) and
+        returned as the packed sdn_aug_params array (host uint8 tensor, pinned if possible)."""
+        n = 2 * batch
+        rec = np.zeros(n, dtype=AUG_DTYPE)
+
+        def factor(j):
+            return self.rng.uniform(max(0.0, 1.0 - j), 1.0 + j, n) if j > 0 else np.ones(n)
+
+        rec["brightness"], rec["contrast"], rec["saturation"] = (factor(j) for j in self.j)
+        if self.hue_jitter > 0:
+            rec["hue"] = self.rng.uniform(-self.hue_jitter, self.hue_jitter, n)
+        if self.gamma_jitter > 0:
+            low = max(0.1, 1.0 - self.gamma_jitter)
+            rec["gamma"] = self.rng.uniform(low, max(low, 1.0 + self.gamma_jitter), n)
+        else:
+            rec["gamma"] = 1.0
+        if self.blur_prob > 0 and self.blur_sigma_max > 0:
+            coin = self.rng.random(n) < self.blur_prob
+            rec["blur_sigma"] = np.where(coin, self.rng.uniform(0.1, max(self.blur_sigma_max, 0.1), n), 0.0)
+        if self.noise_std_max > 0:
+            rec["noise_std"] = self.rng.uniform(0.0, self.noise_std_max, n)
+        rec["noise_seed"] = self.rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32)
+        t = torch.from_numpy(rec.view(np.uint8).copy())
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+
+AUG_DTYPE = np.dtype([("brightness", "<f4"), ("contrast", "<f4"), ("saturation", "<f4"), ("hue", "<f4"),
+                      ("gamma", "<f4"), ("blur_sigma", "<f4"), ("noise_std", "<f4"), ("noise_seed", "<u4")])
+
 
 def pack_aug(views: Sequence[ViewAug]) -> torch.Tensor:
     """Host (pinned when CUDA is present) uint8 tensor holding the sdn_aug_params array."""
@@ -152,9 +182,10 @@ class DevicePreprocessor:
             }
         aug_dev = None
         if aug is not None:
-            if len(aug) != 2 * b:
-                raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {len(aug)}")
-            aug_dev = pack_aug(aug).to(self.device, non_blocking=True)
+            packed = aug if torch.is_tensor(aug) else pack_aug(aug)   # list of ViewAug or sample_packed() output
+            if packed.numel() != 2 * b * 32:
+                raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {packed.numel() // 32}")
+            aug_dev = packed.to(self.device, non_blocking=True)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(
             _lib.load().sdn_preprocess(

@@ -366,7 +366,7 @@ def test_run_epoch_tracks_oracle_curve(dev):
     """A few-hundred-step synthetic training curve: fused CUDA steps (bf16 tensor cores)
     vs the fp32 oracle on the same data and the same AdamW settings.  The two
     trajectories are chaotic relative to each other at the 1e-3 level, so the curve is
-    compared per 20-step segment with an 8 % band."""
+    compared per 20-step segment with an 8 % (+0.01 absolute) band."""
     from stereo_depth_estimation_b200.step import run_epoch
 
     b, h, w, steps, seg = 4, 64, 96, 240, 20
@@ -386,8 +386,9 @@ def test_run_epoch_tracks_oracle_curve(dev):
     assert gs == steps and len(logged) == steps // 10
     assert set(logged[0][1]) == {"train_loss_step", "train_nll_step", "train_mae_step", "train_rmse_step", "train_sigma_step"}
     for a_, r_ in zip(ours, ref):
-        assert a_ == pytest.approx(r_, rel=8e-2), (ours, ref)
-    assert ours[-1] < 0.8 * ours[0] and ref[-1] < 0.8 * ref[0]
+        # the NLL crosses zero late in the run: relative band plus a small absolute floor
+        assert abs(a_ - r_) <= 8e-2 * abs(r_) + 1e-2, (ours, ref)
+    assert ours[-1] < ours[0] - 0.2 and ref[-1] < ref[0] - 0.2
     val, _ = run_epoch(model, batches[:2], dev, optimizer=None)
     oval = so.run_epoch(osd, batches[:2], None)
     assert val["mae"] == pytest.approx(oval["mae"], rel=1.5e-1)
