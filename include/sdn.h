@@ -117,6 +117,10 @@ int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, cons
  * Copies to a host fp32 buffer of B*H_l*W_l*C_l elements; returns the dims. */
 int sdn_debug_read(sdn_ctx* ctx, int which, int kind, float* host_out, int64_t capacity, int* dims4);
 
+/* Timing forensics (SDN_DEBUG_TRACE_LAYER=<conv layer>): clock64() stamps of the three
+ * warp roles of CTA 0 for its first 16 tiles, [role][tile][event] as 384 int64. */
+int sdn_debug_trace(sdn_ctx* ctx, long long* host_out);
+
 /* Per-op device timing: when enabled every op is bracketed by CUDA events on the
  * launching stream.  sdn_profile_dump synchronises the device and writes a CSV
  * "name,layer,calls,total_ms,flops,bytes" (algorithmic flops / bytes of SURVEY 8d

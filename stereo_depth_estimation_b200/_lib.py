@@ -35,6 +35,7 @@ EXPORTS = (
     "sdn_count_valid",
     "sdn_preprocess",
     "sdn_debug_read",
+    "sdn_debug_trace",
     "sdn_profile_enable",
     "sdn_profile_dump",
     "sdn_launch_count",
@@ -99,6 +100,8 @@ def load() -> ctypes.CDLL:
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint, c_void_p]
+    lib.sdn_debug_trace.restype = c_int
+    lib.sdn_debug_trace.argtypes = [c_void_p, c_void_p]
     lib.sdn_profile_enable.restype = c_int
     lib.sdn_profile_enable.argtypes = [c_void_p, c_int]
     lib.sdn_profile_dump.restype = c_int

@@ -26,7 +26,7 @@
 
 namespace sdn {
 
-enum : int { CG_RELU = 1, CG_STATS = 2 };
+enum : int { CG_RELU = 1, CG_STATS = 2, CG_BRES = 4, CG_DBG_NOMMA = 64, CG_DBG_NOEPI = 128, CG_DBG_NOLOADA = 256, CG_DBG_NOSTORE = 512, CG_DBG_NOSTATS = 1024 };
 
 struct CgSeg {
     int8_t map;  // index into a_maps
@@ -55,9 +55,17 @@ struct alignas(64) ConvGemmParams {
     int flags;
     int stages;
     int a_stage_bytes;      // HALO: bytes of one (TH+2) x TW halo box, 1024-aligned
+    int b_res_bytes;        // CG_BRES: the whole packed weight matrix lives in shared memory (loaded once per CTA)
+    int ups;                // HALO: units (k-blocks) per pipeline stage (1 or 3): fewer producer/MMA handshakes per tile
     const float* bias;      // [n_total] or nullptr; added before ReLU
     float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS
+    long long* dbg;         // optional: block 0 records clock64() per role / tile / event (timing forensics)
 };
+#define SDN_DBG(role, tile, ev)                                                              \
+    do {                                                                                     \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (tile) < 16)                              \
+            p.dbg[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                            \
+    } while (0)
 
 template <int SWA, int BLOCK_N>
 struct CgCfg {
@@ -75,12 +83,14 @@ struct CgCfg {
     static constexpr int SCRATCH_BYTES = RG * BLOCK_N * 2 * 4;
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+    static constexpr int DBUF = BLOCK_N <= 64 ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
+    static constexpr int NT = BLOCK_N == 256 ? 2 : 1;    // N tiles a stats layer can have (Cout = 512)
     static constexpr int smem_bytes(int stages) {
-        return 1024 + stages * STAGE_BYTES + D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
+        return 1024 + stages * STAGE_BYTES + DBUF * D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
     }
     // HALO: one stage = one halo A box + the three vertical-tap weight blocks
     static constexpr int smem_bytes_halo(int stages, int a_stage_bytes) {
-        return 1024 + stages * (a_stage_bytes + 3 * B_BYTES) + D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
+        return 1024 + stages * (a_stage_bytes + 3 * B_BYTES) + DBUF * D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
     }
 };
 
@@ -102,18 +112,22 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     uint8_t* stage_base = smem;
+    const bool bres = HALO && (p.flags & CG_BRES) != 0;
     const int a_bytes = HALO ? p.a_stage_bytes : Cfg::A_BYTES;
-    const int stage_bytes = HALO ? p.a_stage_bytes + 3 * Cfg::B_BYTES : Cfg::STAGE_BYTES;
-    uint8_t* stg = smem + stages * stage_bytes;  // D staging, 1024-aligned
-    float* scratch = reinterpret_cast<float*>(stg + Cfg::D_BYTES);
-    float* acc_sum = reinterpret_cast<float*>(stg + Cfg::D_BYTES + Cfg::SCRATCH_BYTES);
-    float* acc_sq = acc_sum + 512;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::D_BYTES + Cfg::SCRATCH_BYTES + Cfg::ACC_BYTES);
+    const int unit_bytes = HALO ? p.a_stage_bytes + (bres ? 0 : 3 * Cfg::B_BYTES) : Cfg::STAGE_BYTES;
+    const int ups = HALO ? p.ups : 1;
+    const int stage_bytes = ups * unit_bytes;
+    uint8_t* b_res = smem + stages * stage_bytes;                 // resident weights (CG_BRES), 1024-aligned
+    uint8_t* stg0 = b_res + (bres ? p.b_res_bytes : 0);           // D staging (DBUF buffers), 1024-aligned
+    float* scratch = reinterpret_cast<float*>(stg0 + Cfg::DBUF * Cfg::D_BYTES);
+    uint64_t* bars =
+        reinterpret_cast<uint64_t*>(stg0 + Cfg::DBUF * Cfg::D_BYTES + Cfg::SCRATCH_BYTES + Cfg::ACC_BYTES);
     uint64_t* full_bar = bars;         // [8]
     uint64_t* empty_bar = bars + 8;    // [8]
     uint64_t* tfull_bar = bars + 16;   // [2]
     uint64_t* tempty_bar = bars + 18;  // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* bres_bar = bars + 20;    // resident-weights arrival
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -129,6 +143,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             ptx::mbar_init(&tfull_bar[a], 1);
             ptx::mbar_init(&tempty_bar[a], 4);
         }
+        ptx::mbar_init(bres_bar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -140,9 +155,6 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
         ptx::tmem_relinquish();
     }
-    if (threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < 1024; i += 128) acc_sum[i] = 0.f;  // acc_sum and acc_sq are contiguous
-    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -153,34 +165,51 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_tile = t % p.n_tiles;
-                const int m_tile = t / p.n_tiles;
-                const int tx = m_tile % p.tiles_x;
-                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-                const int tn = m_tile / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+            int dbg_it = 0;
+            if (bres) {
+                // every k-block's three weight slabs, once: [unit][dy][BLOCK_N][KB]
+                ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(p.kblocks_total) * 3 * Cfg::B_BYTES);
+                for (int u = 0; u < p.kblocks_total; ++u)
+                    ptx::tma_load_3d(b_res + u * 3 * Cfg::B_BYTES, &p.b_map, bres_bar, 0, 0, u * 3);
+            }
+            ptx::TileWalker tw;
+            for (tw.init(blockIdx.x, gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
+                const int n_tile = tw.n_tile;
+                const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
                 int kcount = 0;
+                const int dbg_tile = dbg_it++;
+                SDN_DBG(0, dbg_tile, 0);
+                int sub = 0;   // unit slot inside the current stage
                 for (int sg = 0; sg < p.nsegs; ++sg) {
                     const CgSeg seg = p.segs[sg];
                     for (int cb = 0; cb < seg.cblocks; ++cb) {
-                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                        uint8_t* a_dst = stage_base + s * stage_bytes;
+                        uint8_t* a_dst = stage_base + s * stage_bytes + sub * unit_bytes;
                         uint8_t* b_dst = a_dst + a_bytes;
                         if (HALO) {
                             const uint32_t a_box = uint32_t(p.TW * (p.TH + 2) * SWA);
-                            ptx::mbar_arrive_expect_tx(&full_bar[s], a_box + 3 * Cfg::B_BYTES);
-                            ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
-                                             y0 - 1, n0);
-                            ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
+                            const bool noa = (p.flags & CG_DBG_NOLOADA) != 0;
+                            if (sub == 0) {
+                                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                                ptx::mbar_arrive_expect_tx(&full_bar[s],
+                                                           uint32_t(ups) * ((noa ? 0 : a_box) + (bres ? 0 : 3 * Cfg::B_BYTES)));
+                            }
+                            if (!noa)
+                                ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                                 y0 - 1, n0);
+                            if (!bres) ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
                         } else {
+                            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                             ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                             ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
                                              y0 + seg.dy, n0);
                             ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
                         }
                         ++kcount;
-                        if (++s == stages) { s = 0; ph ^= 1; }
+                        if (kcount <= 7) SDN_DBG(0, dbg_tile, kcount);
+                        if (++sub == ups) {
+                            sub = 0;
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                        }
                     }
                 }
             }
@@ -192,26 +221,37 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             uint32_t ph = 0;
             int a = 0;
             uint32_t aph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            if (bres) ptx::mbar_wait(bres_bar, 0);
+            const uint32_t b_res_addr = ptx::smem_u32(b_res);
+            for (int it = 0; it < my_tiles; ++it) {
+                SDN_DBG(1, it, 0);
                 ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
                 ptx::tc_fence_after();
+                SDN_DBG(1, it, 1);
                 const uint32_t tmem_d = tmem_base + a * BLOCK_N;
-                for (int kb = 0; kb < p.kblocks_total; ++kb) {
+                for (int kb = 0; kb < p.kblocks_total; kb += ups) {
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(stage_base + s * stage_bytes);
-                    const uint32_t b_addr = a_addr + a_bytes;
-                    if (HALO) {
+                    const uint32_t st_addr = ptx::smem_u32(stage_base + s * stage_bytes);
+                    if (p.flags & CG_DBG_NOMMA) {
+                    } else if (HALO) {
+                        for (int j = 0; j < ups; ++j) {
+                            const uint32_t a_addr = st_addr + j * unit_bytes;
+                            const uint32_t b_addr = bres ? b_res_addr + (kb + j) * 3 * Cfg::B_BYTES : a_addr + a_bytes;
 #pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint64_t adesc = ptx::make_smem_desc(a_addr + dy * p.TW * SWA, 16, SBO_A, LAYOUT_A);
-                            const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const uint64_t adesc = ptx::make_smem_desc(a_addr + dy * p.TW * SWA, 16, SBO_A, LAYOUT_A);
+                                const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
-                            for (int k = 0; k < KB / 16; ++k)
-                                ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                 (kb | dy | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < KB / 16; ++k)
+                                    ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                     (kb | j | dy | k) != 0 ? 1u : 0u);
+                            }
                         }
                     } else {
+                        const uint32_t a_addr = st_addr;
+                        const uint32_t b_addr = a_addr + a_bytes;
                         const uint64_t adesc = ptx::make_smem_desc(a_addr, 16, SBO_A, LAYOUT_A);
                         const uint64_t bdesc = ptx::make_smem_desc(b_addr, 16, SBO_A, LAYOUT_A);
 #pragma unroll
@@ -222,9 +262,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                         }
                     }
                     ptx::tc_commit(&empty_bar[s]);
+                    if (kb < 5) SDN_DBG(1, it, 2 + kb);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 ptx::tc_commit(&tfull_bar[a]);
+                SDN_DBG(1, it, 7);
                 a ^= 1;
                 if (a == 0) aph ^= 1;
             }
@@ -234,26 +276,48 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         const int te = threadIdx.x - 64;     // 0..127
         const int quarter = warp & 3;        // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;   // tile row == pixel index in the box
-        const bool do_stats = (p.flags & CG_STATS) != 0;
+        const bool do_stats = (p.flags & CG_STATS) != 0 && !(p.flags & CG_DBG_NOSTATS);
         const bool do_relu = (p.flags & CG_RELU) != 0;
         int a = 0;
         uint32_t aph = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int n_tile = t % p.n_tiles;
-            const int m_tile = t / p.n_tiles;
-            const int tx = m_tile % p.tiles_x;
-            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-            const int tn = m_tile / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+        const int rw = r % p.TW, rh = (r / p.TW) % p.TH, rn = r / (p.TW * p.TH);  // this thread's pixel in the box
+        constexpr int STAT_ROWS = 128 / Cfg::RG;
+        const int st_w = te % Cfg::WPR, st_rg = te / Cfg::WPR;
+        float st_acc[Cfg::NT][Cfg::D_BLOCKS][4];
+#pragma unroll
+        for (int i = 0; i < Cfg::NT; ++i)
+#pragma unroll
+            for (int j = 0; j < Cfg::D_BLOCKS; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st_acc[i][j][k] = 0.f;
+        int sbuf = 0;
+        int dbg_it = 0;
+        const int dmap_div = p.n_tiles_per_dmap;
+        ptx::TileWalker tw;
+        for (tw.init(blockIdx.x, gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
+            const int n_tile = tw.n_tile;
+            const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
 
             // A box row outside the image still sees in-image neighbours through the
             // shifted taps, so its accumulator is not zero: zero it (the TMA store
             // clips it anyway, but the BatchNorm statistics must not see it).
-            const bool row_in_image = (x0 + r % p.TW < p.img_w) && (y0 + (r / p.TW) % p.TH < p.img_h) &&
-                                      (n0 + r / (p.TW * p.TH) < p.img_n);
+            const bool row_in_image = (x0 + rw < p.img_w) && (y0 + rh < p.img_h) && (n0 + rn < p.img_n);
+            uint8_t* stg = stg0 + sbuf * Cfg::D_BYTES;
+            const int dbg_tile = dbg_it++;
+            if (te == 0) SDN_DBG(2, dbg_tile, 0);
+            // the store issued DBUF tiles ago has finished reading this staging buffer
+            if (te == 0) {
+                if (Cfg::DBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else ptx::tma_store_wait_read0();
+            }
+            ptx::named_bar_sync(1, 128);
+            if (te == 0) SDN_DBG(2, dbg_tile, 1);
+
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
+            if (te == 0) SDN_DBG(2, dbg_tile, 2);
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BLOCK_N;
+            if (!(p.flags & CG_DBG_NOEPI))
 #pragma unroll
             for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
                 uint32_t v[32];
@@ -293,12 +357,15 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[a]);
+            if (te == 0) SDN_DBG(2, dbg_tile, 3);
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(1, 128);
+            if (te == 0) SDN_DBG(2, dbg_tile, 4);
 
-            if (te == 0) {
-                const int dmap = n_tile / p.n_tiles_per_dmap;
-                const int cbase = (n_tile % p.n_tiles_per_dmap) * BLOCK_N;
+            if (te == 0 && !(p.flags & CG_DBG_NOSTORE)) {
+                int dmap = 0, nrem = n_tile;   // n_tile / n_tiles_per_dmap without a division (<= 4 maps)
+                while (nrem >= dmap_div) { nrem -= dmap_div; ++dmap; }
+                const int cbase = nrem * BLOCK_N;
 #pragma unroll
                 for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk)
                     ptx::tma_store_4d(&p.d_maps[dmap], stg + cbk * Cfg::D_BLOCK_BYTES, cbase + cbk * Cfg::DCH, x0, y0,
@@ -306,55 +373,65 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                 ptx::tma_store_commit();
             }
             if (do_stats) {
-                // per-channel sum / sum of squares of the bf16 values just staged
-                // (== what the next kernel will read back), reduced over the 128 rows
-                const int w = te % Cfg::WPR;
-                const int rg = te / Cfg::WPR;
-                constexpr int ROWS = 128 / Cfg::RG;
+                // per-channel sum / sum of squares of the bf16 values just staged (== what the
+                // next kernel reads back).  Each thread owns one 32-bit word column (2 channels)
+                // of one row group and keeps its partials in REGISTERS across tiles; the
+                // cross-thread reduction happens once, after the tile loop.
 #pragma unroll
                 for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                     const uint8_t* blk = stg + cbk * Cfg::D_BLOCK_BYTES;
-#pragma unroll 4
-                    for (int rr = 0; rr < ROWS; ++rr) {
-                        const int row = rg * ROWS + rr;
-                        const int j = w >> 2;
+#pragma unroll 8
+                    for (int rr = 0; rr < STAT_ROWS; ++rr) {
+                        const int row = st_rg * STAT_ROWS + rr;
+                        const int j = st_w >> 2;
                         const int sw = (Cfg::SWD == 128) ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3));
                         const uint32_t u =
-                            *reinterpret_cast<const uint32_t*>(blk + row * Cfg::SWD + (sw << 4) + ((w & 3) << 2));
+                            *reinterpret_cast<const uint32_t*>(blk + row * Cfg::SWD + (sw << 4) + ((st_w & 3) << 2));
                         const float lo = __uint_as_float(u << 16);
                         const float hi = __uint_as_float(u & 0xFFFF0000u);
                         s0 += lo; q0 = fmaf(lo, lo, q0);
                         s1 += hi; q1 = fmaf(hi, hi, q1);
                     }
-                    const int chn = cbk * Cfg::DCH + 2 * w;
-                    scratch[rg * BLOCK_N + chn] = s0;
-                    scratch[rg * BLOCK_N + chn + 1] = s1;
-                    scratch[Cfg::RG * BLOCK_N + rg * BLOCK_N + chn] = q0;
-                    scratch[Cfg::RG * BLOCK_N + rg * BLOCK_N + chn + 1] = q1;
-                }
-                ptx::named_bar_sync(2, 128);
-                for (int c = te; c < BLOCK_N; c += 128) {
-                    float s = 0.f, q = 0.f;
 #pragma unroll
-                    for (int g = 0; g < Cfg::RG; ++g) {
-                        s += scratch[g * BLOCK_N + c];
-                        q += scratch[Cfg::RG * BLOCK_N + g * BLOCK_N + c];
-                    }
-                    acc_sum[n_tile * BLOCK_N + c] += s;
-                    acc_sq[n_tile * BLOCK_N + c] += q;
+                    for (int nt = 0; nt < Cfg::NT; ++nt)
+                        if (nt == n_tile || Cfg::NT == 1) {
+                            st_acc[nt][cbk][0] += s0; st_acc[nt][cbk][1] += s1;
+                            st_acc[nt][cbk][2] += q0; st_acc[nt][cbk][3] += q1;
+                        }
                 }
             }
-            if (te == 0) ptx::tma_store_wait_read0();
-            ptx::named_bar_sync(1, 128);
+            if (te == 0) SDN_DBG(2, dbg_tile, 5);
+            sbuf = (Cfg::DBUF == 2) ? (sbuf ^ 1) : 0;
             a ^= 1;
             if (a == 0) aph ^= 1;
         }
         if (do_stats) {
+            // one cross-row-group reduction per kernel: scratch[rg][channel] -> per-CTA partials
             float* dst = p.stats_partials + size_t(blockIdx.x) * 2 * p.n_total;
-            for (int c = te; c < p.n_total; c += 128) {
-                dst[c] = acc_sum[c];
-                dst[p.n_total + c] = acc_sq[c];
+#pragma unroll
+            for (int nt = 0; nt < Cfg::NT; ++nt) {
+                if (nt * BLOCK_N >= p.n_total) break;
+                ptx::named_bar_sync(2, 128);
+#pragma unroll
+                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
+                    const int chn = cbk * Cfg::DCH + 2 * st_w;
+                    scratch[st_rg * BLOCK_N + chn] = st_acc[nt][cbk][0];
+                    scratch[st_rg * BLOCK_N + chn + 1] = st_acc[nt][cbk][1];
+                    scratch[Cfg::RG * BLOCK_N + st_rg * BLOCK_N + chn] = st_acc[nt][cbk][2];
+                    scratch[Cfg::RG * BLOCK_N + st_rg * BLOCK_N + chn + 1] = st_acc[nt][cbk][3];
+                }
+                ptx::named_bar_sync(2, 128);
+                for (int c = te; c < BLOCK_N; c += 128) {
+                    float sum = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int g = 0; g < Cfg::RG; ++g) {
+                        sum += scratch[g * BLOCK_N + c];
+                        sq += scratch[Cfg::RG * BLOCK_N + g * BLOCK_N + c];
+                    }
+                    dst[nt * BLOCK_N + c] = sum;
+                    dst[p.n_total + nt * BLOCK_N + c] = sq;
+                }
             }
         }
         if (te == 0) ptx::tma_store_wait0();

@@ -102,15 +102,17 @@ __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict_
 constexpr int IM2COL_PX = 128;
 constexpr int IM2COL_MAXC = 8;
 
+template <int Cin>
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
-                                                           int Cin, int H, int W) {
+                                                           int H, int W) {
     __shared__ float tile[IM2COL_MAXC * 3][IM2COL_PX + 2];
     const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
     const int xb = blockIdx.x % xblocks;
     const int yh = (blockIdx.x / xblocks) % H;
     const int n = blockIdx.x / (xblocks * H);
     const int x0 = xb * IM2COL_PX;
-    const int K = 9 * Cin;
+    constexpr int K = 9 * Cin;
+    static_assert(Cin <= IM2COL_MAXC, "first-layer channel count");
     for (int i = threadIdx.x; i < Cin * 3 * (IM2COL_PX + 2); i += blockDim.x) {
         const int col = i % (IM2COL_PX + 2);
         const int row = i / (IM2COL_PX + 2);  // c * 3 + dy
@@ -251,16 +253,15 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
 // Pass 1 (reduce): per-channel sum(dz), sum(dz * xhat)  -> per-block partials.
 // Pass 2 (apply) : dy = scale * (dz - c1 - xhat * c2)  with c1 = sum(dz)/M,
 //                  c2 = sum(dz*xhat)/M (training mode batch-norm backward).
-struct BnBwdQuad {
-    float dz[4][8];
-    float xh[4][8];
-};
-
-template <bool POOL>
-__device__ __forceinline__ void bn_bwd_load(const bf16* __restrict__ y, const bf16* __restrict__ g,
-                                            const bf16* __restrict__ gp, const float* sc, const float* sh,
-                                            const float* mu, const float* rs, long long i, int B, int H, int W, int C,
-                                            BnBwdQuad& o, long long (&pix)[4]) {
+// One work item = 8 channels of one pixel (or of one 2x2 quad when POOL).  APPLY = false:
+// accumulate the two per-channel sums; APPLY = true: write dy.  The quad variant keeps only
+// the raw bf16 y vectors and the running arg-max in registers (two passes over the quad).
+template <bool POOL, bool APPLY>
+__device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf16* __restrict__ g,
+                                            const bf16* __restrict__ gp, const float (&sc)[8], const float (&sh)[8],
+                                            const float (&mu)[8], const float (&rs)[8], const float (&k1)[8],
+                                            const float (&k2)[8], long long i, int H, int W, int C, float (&s1)[8],
+                                            float (&s2)[8], bf16* __restrict__ dy) {
     const int CG = C >> 3;
     const int cg = int(i % CG);
     if (POOL) {
@@ -269,53 +270,59 @@ __device__ __forceinline__ void bn_bwd_load(const bf16* __restrict__ y, const bf
         const int x2 = int(qd % W2);
         const int y2 = int((qd / W2) % H2);
         const int n = int(qd / ((long long)W2 * H2));
-        float gpf[8];
-        unpack8(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gpf);
-        float z[4][8], ab[4][8];
+        const long long p00 = ((long long)n * H + 2 * y2) * W + 2 * x2;
+        const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+        uint4 yr[4];
+        float best[8];
+        int am[8];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            pix[d] = ((long long)n * H + (2 * y2 + (d >> 1))) * W + (2 * x2 + (d & 1));
-            float yf[8], gf[8];
-            unpack8(ldg16(y + pix[d] * C + cg * 8), yf);
+            yr[d] = ldg16(y + pix[d] * C + cg * 8);
+            float yf[8];
+            unpack8(yr[d], yf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // the forward pooled the bf16-rounded activation: reproduce it for the arg-max
+                const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yf[j], sc[j], sh[j]), 0.f)));
+                if (d == 0 || a > best[j]) { best[j] = a; am[j] = d; }   // first maximum wins ties
+            }
+        }
+        float gpf[8];
+        unpack8(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gpf);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            float yf[8], gf[8], o[8];
+            unpack8(yr[d], yf);
             unpack8(ldg16(g + pix[d] * C + cg * 8), gf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                z[d][j] = fmaf(yf[j], sc[j], sh[j]);
-                // the forward pooled the bf16-rounded activation: reproduce it for the arg-max
-                ab[d][j] = __bfloat162float(__float2bfloat16_rn(fmaxf(z[d][j], 0.f)));
-                o.xh[d][j] = (yf[j] - mu[j]) * rs[j];
-                o.dz[d][j] = gf[j];
+                const float z = fmaf(yf[j], sc[j], sh[j]);
+                const float da = gf[j] + (am[j] == d ? gpf[j] : 0.f);
+                const float dz = z > 0.f ? da : 0.f;
+                const float xh = (yf[j] - mu[j]) * rs[j];
+                if (APPLY) o[j] = sc[j] * (dz - k1[j] - xh * k2[j]);
+                else { s1[j] += dz; s2[j] = fmaf(dz, xh, s2[j]); }
             }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int am = 0;
-            float best = ab[0][j];
-#pragma unroll
-            for (int d = 1; d < 4; ++d)
-                if (ab[d][j] > best) { best = ab[d][j]; am = d; }
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                float da = o.dz[d][j] + (d == am ? gpf[j] : 0.f);
-                o.dz[d][j] = z[d][j] > 0.f ? da : 0.f;
-            }
+            if (APPLY) *reinterpret_cast<uint4*>(dy + pix[d] * C + cg * 8) = pack8(o);
         }
     } else {
-        pix[0] = i / CG;
-        float yf[8], gf[8];
+        float yf[8], gf[8], o[8];
         unpack8(ldg16(y + i * 8), yf);
         unpack8(ldg16(g + i * 8), gf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float z = fmaf(yf[j], sc[j], sh[j]);
-            o.xh[0][j] = (yf[j] - mu[j]) * rs[j];
-            o.dz[0][j] = z > 0.f ? gf[j] : 0.f;
+            const float dz = z > 0.f ? gf[j] : 0.f;
+            const float xh = (yf[j] - mu[j]) * rs[j];
+            if (APPLY) o[j] = sc[j] * (dz - k1[j] - xh * k2[j]);
+            else { s1[j] += dz; s2[j] = fmaf(dz, xh, s2[j]); }
         }
+        if (APPLY) *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
     }
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
                                                             const bf16* __restrict__ gp,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
@@ -326,26 +333,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = int(tid0 % CG);  // fixed per thread: the stride is a multiple of CG
-    float sc[8], sh[8], mu[8], rs[8];
+    float sc[8], sh[8], mu[8], rs[8], s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
+        s1[j] = 0.f; s2[j] = 0.f;
     }
-    float s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x) {
-        BnBwdQuad q;
-        long long pix[4];
-        bn_bwd_load<POOL>(y, g, gp, sc, sh, mu, rs, i, B, H, W, C, q, pix);
-#pragma unroll
-        for (int d = 0; d < (POOL ? 4 : 1); ++d)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                s1[j] += q.dz[d][j];
-                s2[j] = fmaf(q.dz[d][j], q.xh[d][j], s2[j]);
-            }
-    }
+    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
+        bn_bwd_item<POOL, false>(y, g, gp, sc, sh, mu, rs, sc, sc, i, H, W, C, s1, s2, nullptr);
     __shared__ float red[256][17];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
@@ -379,7 +374,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
+__global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
                                                            const bf16* __restrict__ gp,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
@@ -391,24 +386,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = int(tid0 % CG);
-    float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+    float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8], s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
         k1[j] = c1[cg * 8 + j]; k2[j] = c2[cg * 8 + j];
     }
-    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x) {
-        BnBwdQuad q;
-        long long pix[4];
-        bn_bwd_load<POOL>(y, g, gp, sc, sh, mu, rs, i, B, H, W, C, q, pix);
-#pragma unroll
-        for (int d = 0; d < (POOL ? 4 : 1); ++d) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = sc[j] * (q.dz[d][j] - k1[j] - q.xh[d][j] * k2[j]);
-            *reinterpret_cast<uint4*>(dy + pix[d] * C + cg * 8) = pack8(o);
-        }
-    }
+    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
+        bn_bwd_item<POOL, true>(y, g, gp, sc, sh, mu, rs, k1, k2, i, H, W, C, s1, s2, dy);
 }
 
 // Per-channel column sum of an NHWC bf16 tensor (ConvTranspose2d bias gradient).

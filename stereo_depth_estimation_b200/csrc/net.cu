@@ -209,6 +209,7 @@ struct sdn_ctx {
     int64_t* bn_nbt[SDN_NUM_BN] = {};
     bool have_params = false, have_forward_train = false;
     bool pre_only = false;  // SDN_CTX_PREPROCESS_ONLY: no network workspace
+    long long* dbg = nullptr;  // timing forensics buffer (3 roles x 16 tiles x 8 events)
     int accumulate = 0;
     int64_t launches = 0;
     // optional per-op timing (CUDA events on the launching stream)
@@ -451,8 +452,20 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     if ((flags & CG_STATS) && n_total > 512) return fail("build_gemm: stats need n_total <= 512");
     int stages = 8;
     if (op.halo) {
-        while (stages > 2 && cg_smem_halo(op.swa, bn, stages, p.a_stage_bytes) > 220 * 1024) --stages;
-        op.smem = cg_smem_halo(op.swa, bn, stages, p.a_stage_bytes);
+        // weights resident in shared memory when the whole packed matrix of this N tile fits;
+        // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
+        const int b_total = kblocks * 3 * bn * op.swa;
+        static int bres_max = -1, ups_on = -1;
+        if (bres_max < 0) { const char* e = getenv("SDN_BRES_MAXKB"); bres_max = (e ? atoi(e) : 80) * 1024; }
+        if (ups_on < 0) { const char* e = getenv("SDN_UPS"); ups_on = e ? atoi(e) : 3; }
+        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);   // staging, scratch, barriers
+        const bool res = p.n_tiles == 1 && b_total <= bres_max;
+        if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
+        const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn * op.swa);
+        const int budget = 220 * 1024 - fixed - (res ? b_total : 0);
+        p.ups = (ups_on == 3 && kblocks % 3 == 0 && budget / (3 * unit_bytes) >= 4) ? 3 : 1;
+        stages = std::max(2, std::min(8, budget / (p.ups * unit_bytes)));
+        op.smem = fixed + (res ? b_total : 0) + stages * p.ups * unit_bytes;
     } else {
         while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
         op.smem = cg_smem(op.swa, bn, stages);
@@ -631,6 +644,7 @@ static int plan_and_alloc(sdn_ctx* c) {
         carve(cur, (size_t)c->num_sms * 2 * 512 * sizeof(float), (void**)&c->stats_partials);
         carve(cur, (size_t)BWD_BLOCKS * 2 * 512 * sizeof(float), (void**)&c->bwd_partials);
         carve(cur, 128 * sizeof(float), (void**)&c->head_grads);
+        carve(cur, 3 * 16 * 8 * sizeof(long long), (void**)&c->dbg);
         carve(cur, 64, (void**)&c->n_local);
         const int parts = ((c->W + 127) / 128) * ((c->H + PRE_ROWS - 1) / PRE_ROWS);
         carve(cur, (size_t)2 * B * parts * sizeof(float), (void**)&c->gray_part);
@@ -799,7 +813,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     {
         const double px = (double)B * H * W;
         ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + 64 * 2));
-        im2col_first_kernel<<<B * H * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st>>>(x, c->x0.p, B, 6, H, W);
+        im2col_first_kernel<6><<<B * H * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st>>>(x, c->x0.p, B, H, W);
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
@@ -813,7 +827,15 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             SDN_OK(launch_cg(c, U.fprop, st));
         }
         GemmOp op = L.fprop;
-        op.p.flags = training ? CG_STATS : 0;
+        op.p.flags = (op.p.flags & ~CG_STATS) | (training ? CG_STATS : 0);
+        {
+            static int dbg = -1;
+            if (dbg < 0) { const char* e = getenv("SDN_DEBUG_ABLATE"); dbg = e ? atoi(e) : 0; }
+            op.p.flags |= dbg;   // timing experiments only (results are garbage)
+            static int dbg_layer = -2;
+            if (dbg_layer == -2) { const char* e = getenv("SDN_DEBUG_TRACE_LAYER"); dbg_layer = e ? atoi(e) : -1; }
+            op.p.dbg = (i == dbg_layer) ? c->dbg : nullptr;
+        }
         {
             const double px = (double)B * L.y.H * L.y.W;
             ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
@@ -1175,6 +1197,14 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdn_debug_trace(sdn_ctx* c, long long* host_out) {
+    if (c == nullptr || host_out == nullptr) return fail("sdn_debug_trace: NULL argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, c->dbg, 3 * 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

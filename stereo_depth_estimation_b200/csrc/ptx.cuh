@@ -173,6 +173,35 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
            (uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46) | (uint64_t(layout_type) << 61);
 }
 
+// Walks tile indices t0, t0+step, ... of a (n_tile fastest, then x, y, image) tile
+// grid WITHOUT per-tile integer divisions: runtime div/mod costs a ~100-cycle
+// dependent instruction chain on the single producer / MMA / epilogue thread,
+// which at 3 k-blocks per tile was the dominant per-tile cost.
+struct TileWalker {
+    int n_tile, tx, ty, tn;
+    int dn, dx, dy, dt;
+    int n_tiles, tiles_x, tiles_y;
+    int remaining;
+    __device__ __forceinline__ void init(int t0, int step, int total, int n_tiles_, int tiles_x_, int tiles_y_) {
+        n_tiles = n_tiles_; tiles_x = tiles_x_; tiles_y = tiles_y_;
+        remaining = t0 < total ? (total - t0 + step - 1) / step : 0;
+        n_tile = t0 % n_tiles; int m = t0 / n_tiles;
+        tx = m % tiles_x; m /= tiles_x;
+        ty = m % tiles_y; tn = m / tiles_y;
+        dn = step % n_tiles; m = step / n_tiles;
+        dx = m % tiles_x; m /= tiles_x;
+        dy = m % tiles_y; dt = m / tiles_y;
+    }
+    __device__ __forceinline__ bool valid() const { return remaining > 0; }
+    __device__ __forceinline__ void next() {
+        --remaining;
+        n_tile += dn; int c = n_tile >= n_tiles ? 1 : 0; n_tile -= c * n_tiles;
+        tx += dx + c; c = tx >= tiles_x ? 1 : 0; tx -= c * tiles_x;
+        ty += dy + c; c = ty >= tiles_y ? 1 : 0; ty -= c * tiles_y;
+        tn += dt + c;
+    }
+};
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    int my_tiles = 0;
-    for (int t = blockIdx.x; t < ptiles; t += gridDim.x) ++my_tiles;
+    const int my_tiles = (int)blockIdx.x < ptiles ? (ptiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -108,11 +107,19 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             int s = 0;
             uint32_t ph = 0;
             const uint32_t tx_bytes = p.a_atoms * a_tile_bytes + nunits * (b_rows * SWB);
-            for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
-                const int tx = t % p.tiles_x;
-                const int ty = (t / p.tiles_x) % p.tiles_y;
-                const int tn = t / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+            // per-unit constants, decoded once (no divisions inside the pixel-tile loop)
+            int u_src[8], u_c0[8], u_dx[8];
+            for (int g = 0; g < nunits; ++g) {
+                const int u = unit0 + g;
+                const int dxi = p.halo ? u / p.atoms_per_tap : 1;
+                const int ca = p.halo ? u % p.atoms_per_tap : u;
+                u_src[g] = ca < p.atoms_src0 ? 0 : 1;
+                u_c0[g] = (u_src[g] == 0 ? ca : ca - p.atoms_src0) * CA;
+                u_dx[g] = dxi - 1;
+            }
+            ptx::TileWalker tw;
+            for (tw.init(blockIdx.x, gridDim.x, ptiles, 1, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
+                const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
                 ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * stage_bytes;
                 uint8_t* b_dst = a_dst + p.a_atoms * a_tile_bytes;
@@ -120,15 +127,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 for (int i = 0; i < p.a_atoms; ++i)
                     ptx::tma_load_4d(a_dst + i * a_tile_bytes, &p.a_maps[variant], &full_bar[s],
                                      m_tile * 128 + i * 64, x0, y0, n0);
-                for (int g = 0; g < nunits; ++g) {
-                    const int u = unit0 + g;
-                    const int dxi = p.halo ? u / p.atoms_per_tap : 1;
-                    const int ca = p.halo ? u % p.atoms_per_tap : u;
-                    const int src = ca < p.atoms_src0 ? 0 : 1;
-                    const int c0 = (src == 0 ? ca : ca - p.atoms_src0) * CA;
-                    ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[src], &full_bar[s], c0, x0 + dxi - 1,
-                                     y0 - p.halo, n0);
-                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (g < nunits)
+                        ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[u_src[g]], &full_bar[s], u_c0[g],
+                                         x0 + u_dx[g], y0 - p.halo, n0);
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
