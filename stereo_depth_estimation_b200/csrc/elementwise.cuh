@@ -50,14 +50,17 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 // row-halo K order (conv_gemm HALO): k = ((dx*blocks + cb)*3 + dy)*KB + c, channel = cb*KB + c, tap = dy*3 + dx
 // mode 5: conv3x3 forward   dst[co][k]                    = W[co][channel][tap]           (Kpad = KB)
 // mode 6: conv3x3 dgrad     dst[ci][k]                    = W[channel][ci][8 - tap]       (Kpad = KB)
+// oscale (modes 0, 2, 5 only): per-output-channel factor folded into the packed weights
+// (eval-mode BatchNorm: w' = w * gamma / sqrt(running_var + eps)); nullptr = 1.
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int mode, int Co, int Ci,
-                                   int Kpad) {
+                                   int Kpad, const float* __restrict__ oscale) {
     const int total = (mode == 2) ? Co * Kpad : ((mode == 3 || mode == 4) ? 4 * Co * Ci : 9 * Co * Ci);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (mode == 0) {
             const int co = i / (9 * Ci), rem = i % (9 * Ci), tap = rem / Ci, ci = rem % Ci;
             v = w[(co * Ci + ci) * 9 + tap];
+            if (oscale != nullptr) v *= oscale[co];
         } else if (mode == 1) {
             const int ci = i / (9 * Co), rem = i % (9 * Co), tap = rem / Co, co = rem % Co;
             v = w[(co * Ci + ci) * 9 + (8 - tap)];
@@ -66,6 +69,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
             if (k < 9 * Ci) {
                 const int tap = k / Ci, ci = k % Ci;
                 v = w[(co * Ci + ci) * 9 + tap];
+                if (oscale != nullptr) v *= oscale[co];
             }
         } else if (mode == 5 || mode == 6) {
             const int KB = Kpad;
@@ -76,6 +80,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
             const int dx = unit / blocks, cb = unit % blocks;
             const int chan = cb * KB + c, tap = dy * 3 + dx;
             v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
+            if (mode == 5 && oscale != nullptr) v *= oscale[row];
         } else if (mode == 3) {
             const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
             v = w[(ci * Co + co) * 4 + q];
@@ -242,6 +247,31 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
                 f[j] = fmaxf(fmaf(f[j], __ldg(scale + cg * 8 + j), __ldg(shift + cg * 8 + j)), 0.f);
             *reinterpret_cast<uint4*>(a + i * 8) = pack8(f);
         }
+    }
+}
+
+// 2x2 max pool of an NHWC bf16 tensor (eval path: BN+ReLU already applied by the conv epilogue).
+__global__ void maxpool2x2_kernel(const bf16* __restrict__ a, bf16* __restrict__ pooled, int B, int H, int W, int C) {
+    const int CG = C >> 3, H2 = H >> 1, W2 = W >> 1;
+    const long long total = (long long)B * H2 * W2 * CG;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cg = int(i % CG);
+        const long long qd = i / CG;
+        const int x2 = int(qd % W2);
+        const int y2 = int((qd / W2) % H2);
+        const int n = int(qd / ((long long)W2 * H2));
+        const long long p00 = ((long long)n * H + 2 * y2) * W + 2 * x2;
+        float m[8], f[8];
+        unpack8(ldg16(a + p00 * C + cg * 8), m);
+        const long long nb[3] = {p00 + 1, p00 + W, p00 + W + 1};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            unpack8(ldg16(a + nb[d] * C + cg * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        }
+        *reinterpret_cast<uint4*>(pooled + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8) = pack8(m);
     }
 }
 

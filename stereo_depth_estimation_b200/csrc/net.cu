@@ -167,7 +167,7 @@ struct ConvL {  // conv3x3 + BatchNorm + ReLU
     bf16 *wf = nullptr, *wd = nullptr;
     float *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr, *c1 = nullptr, *c2 = nullptr;
     float* wg = nullptr;  // fp32 weight-gradient workspace [9*cin][cout]
-    GemmOp fprop, dgrad;
+    GemmOp fprop, fprop_eval, dgrad;   // fprop_eval: BN folded, epilogue = +shift, ReLU, writes `a` directly
     WgradOp wgrad;
     bool has_dgrad = true;
 };
@@ -390,9 +390,14 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     const int KB = op.swa / 2;
     int bn = std::min(n_per_dmap, 256);
     if (op.swa == 64 && bn > 64) bn = 64;
+    const int W = dviews[0].W, H = dviews[0].H;
+    if (!(flags & CG_STATS)) {
+        // latency regime (few pixels): narrower N tiles spread the K loop over more CTAs
+        const long long m_est = ((long long)W * H * B + 127) / 128;
+        while (bn > 32 && m_est * (n_total / bn) < c->num_sms / 2) bn /= 2;
+    }
     if (n_per_dmap % bn != 0) return fail("build_gemm: N %d not divisible by BLOCK_N %d", n_per_dmap, bn);
     op.block_n = bn;
-    const int W = dviews[0].W, H = dviews[0].H;
     op.halo = conv3x3 && bn <= g_halo_max_n;
     Tile t = choose_tile(W, H, B, 128);
     if (op.halo) {
@@ -695,6 +700,8 @@ static int prepare_batch(sdn_ctx* c, int B) {
         }
         SDN_OK(build_gemm(c, L.fprop, B, av, segs, L.wf, L.cout, {full_view(L.y)}, L.cout, nullptr, CG_STATS,
                           c->stats_partials, !L.first));
+        SDN_OK(build_gemm(c, L.fprop_eval, B, av, segs, L.wf, L.cout, {full_view(L.a)}, L.cout, L.shift, CG_RELU,
+                          nullptr, !L.first));
         // ---- data gradient: conv3x3 of dy with flipped / transposed weights
         if (L.has_dgrad) {
             std::vector<SegSpec> dsegs(k3x3, k3x3 + 9);
@@ -743,21 +750,23 @@ static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
 
 // bf16 operand cache <- fp32 parameters
 static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
+    const bool fold = !training;   // eval: BatchNorm scale folded into the forward weights
     ProfScope ps(c, st, "pack_weights", 0, 0.0, 7763938.0 * (4 + 2) * (training ? 2 : 1));
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
         const float* w = c->params[L.p_w];
         if (L.first) {
-            pack_weight_kernel<<<ew_grid(c, L.cout * 64, 256), 256, 0, st>>>(w, L.wf, 2, L.cout, L.cin, 64);
+            pack_weight_kernel<<<ew_grid(c, L.cout * 64, 256), 256, 0, st>>>(w, L.wf, 2, L.cout, L.cin, 64,
+                                                                            fold ? L.scale : nullptr);
             ++c->launches;
         } else {
             const int n = 9 * L.cin * L.cout;
             pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wf, L.fprop.halo ? 5 : 0, L.cout, L.cin,
-                                                                   L.fprop.swa / 2);
+                                                                   L.fprop.swa / 2, fold ? L.scale : nullptr);
             ++c->launches;
             if (training) {
                 pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wd, L.dgrad.halo ? 6 : 1, L.cout, L.cin,
-                                                                       L.dgrad.swa / 2);
+                                                                       L.dgrad.swa / 2, nullptr);
                 ++c->launches;
             }
         }
@@ -765,10 +774,10 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
     for (int k = 0; k < 4; ++k) {
         UpL& U = c->up[k];
         const int n = 4 * U.cin * U.cout;
-        pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wf, 3, U.cout, U.cin, 0);
+        pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wf, 3, U.cout, U.cin, 0, nullptr);
         ++c->launches;
         if (training) {
-            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wd, 4, U.cout, U.cin, 0);
+            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wd, 4, U.cout, U.cin, 0, nullptr);
             ++c->launches;
         }
         tile_bias_kernel<<<1, 256, 0, st>>>(c->params[U.p_b], U.bias4, U.cout, 4);
@@ -799,8 +808,8 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     if (c->pre_only) return fail("sdn_forward: context was created with SDN_CTX_PREPROCESS_ONLY");
     if (!c->have_params) return fail("sdn_forward: call sdn_set_params first");
     SDN_OK(prepare_batch(c, B));
-    if (dirty) SDN_OK(pack_params(c, training != 0, st));
-    if (!training) {
+    if (!training && dirty) {
+        // eval: scale/shift from the running statistics, folded into the weights at pack time
         for (int i = 0; i < 18; ++i) {
             ConvL& L = c->conv[i];
             bn_prepare_eval_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(L.cout, c->params[L.p_gamma],
@@ -809,6 +818,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             ++c->launches;
         }
     }
+    if (dirty) SDN_OK(pack_params(c, training != 0, st));
     const int H = c->H, W = c->W;
     {
         const double px = (double)B * H * W;
@@ -826,8 +836,23 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
                          px * (U.cin + 4 * U.cout) * 2);
             SDN_OK(launch_cg(c, U.fprop, st));
         }
+        if (!training) {
+            const double px = (double)B * L.y.H * L.y.W;
+            {
+                ProfScope ps(c, st, "conv_fprop_eval", i, 2.0 * px * L.cout * 9 * L.cin,
+                             px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+                SDN_OK(launch_cg(c, L.fprop_eval, st));
+            }
+            if (L.pooled_out) {
+                ProfScope ps(c, st, "maxpool", i, 0.0, px * L.cout * 2 * 1.25);
+                const long long items = (long long)B * (L.y.H / 2) * (L.y.W / 2) * (L.cout / 8);
+                maxpool2x2_kernel<<<ew_grid(c, items, 256), 256, 0, st>>>(L.a.p, L.pool.p, B, L.y.H, L.y.W, L.cout);
+                ++c->launches;
+            }
+            continue;
+        }
         GemmOp op = L.fprop;
-        op.p.flags = (op.p.flags & ~CG_STATS) | (training ? CG_STATS : 0);
+        op.p.flags = (op.p.flags & ~CG_STATS) | CG_STATS;
         {
             static int dbg = -1;
             if (dbg < 0) { const char* e = getenv("SDN_DEBUG_ABLATE"); dbg = e ? atoi(e) : 0; }
