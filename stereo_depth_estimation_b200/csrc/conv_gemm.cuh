@@ -162,11 +162,12 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
-        if (lane == 0) {
+        // converged warp; one elected lane issues the mbarrier arrive and the TMA instructions
+        {
             int s = 0;
             uint32_t ph = 0;
             int dbg_it = 0;
-            if (bres) {
+            if (bres && ptx::elect_one()) {
                 // every k-block's three weight slabs, once: [unit][dy][BLOCK_N][KB]
                 ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(p.kblocks_total) * 3 * Cfg::B_BYTES);
                 for (int u = 0; u < p.kblocks_total; ++u)
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                 const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
                 int kcount = 0;
                 const int dbg_tile = dbg_it++;
-                SDN_DBG(0, dbg_tile, 0);
+                if (lane == 0) SDN_DBG(0, dbg_tile, 0);
                 int sub = 0;   // unit slot inside the current stage
                 for (int sg = 0; sg < p.nsegs; ++sg) {
                     const CgSeg seg = p.segs[sg];
@@ -188,24 +189,29 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                         if (HALO) {
                             const uint32_t a_box = uint32_t(p.TW * (p.TH + 2) * SWA);
                             const bool noa = (p.flags & CG_DBG_NOLOADA) != 0;
-                            if (sub == 0) {
-                                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                                ptx::mbar_arrive_expect_tx(&full_bar[s],
-                                                           uint32_t(ups) * ((noa ? 0 : a_box) + (bres ? 0 : 3 * Cfg::B_BYTES)));
+                            if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                            if (ptx::elect_one()) {
+                                if (sub == 0)
+                                    ptx::mbar_arrive_expect_tx(
+                                        &full_bar[s], uint32_t(ups) * ((noa ? 0 : a_box) + (bres ? 0 : 3 * Cfg::B_BYTES)));
+                                if (!noa)
+                                    ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB,
+                                                     x0 + seg.dx, y0 - 1, n0);
+                                if (!bres)
+                                    ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
                             }
-                            if (!noa)
-                                ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
-                                                 y0 - 1, n0);
-                            if (!bres) ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
                         } else {
                             ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                            ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                            ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
-                                             y0 + seg.dy, n0);
-                            ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                            if (ptx::elect_one()) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                                ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                                 y0 + seg.dy, n0);
+                                ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                            }
                         }
+                        __syncwarp();
                         ++kcount;
-                        if (kcount <= 7) SDN_DBG(0, dbg_tile, kcount);
+                        if (lane == 0 && kcount <= 7) SDN_DBG(0, dbg_tile, kcount);
                         if (++sub == ups) {
                             sub = 0;
                             if (++s == stages) { s = 0; ph ^= 1; }
@@ -216,7 +222,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the loop converged so the descriptor arithmetic stays in uniform
+        // registers; only the tcgen05 instructions themselves are issued by one elected lane.
+        {
             int s = 0;
             uint32_t ph = 0;
             int a = 0;
@@ -225,10 +233,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             if (bres) ptx::mbar_wait(bres_bar, 0);
             const uint32_t b_res_addr = ptx::smem_u32(b_res);
             for (int it = 0; it < my_tiles; ++it) {
-                SDN_DBG(1, it, 0);
+                if (lane == 0) SDN_DBG(1, it, 0);
                 ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
                 ptx::tc_fence_after();
-                SDN_DBG(1, it, 1);
+                if (lane == 0) SDN_DBG(1, it, 1);
                 const uint32_t tmem_d = tmem_base + a * BLOCK_N;
                 for (int kb = 0; kb < p.kblocks_total; kb += ups) {
                     ptx::mbar_wait(&full_bar[s], ph);
@@ -245,8 +253,9 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                                 const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                     (kb | j | dy | k) != 0 ? 1u : 0u);
+                                    if (ptx::elect_one())
+                                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                         (kb | j | dy | k) != 0 ? 1u : 0u);
                             }
                         }
                     } else {
@@ -257,16 +266,18 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k) {
                             // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-                            ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                             (kb | k) != 0 ? 1u : 0u);
+                            if (ptx::elect_one())
+                                ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                 (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    ptx::tc_commit(&empty_bar[s]);
-                    if (kb < 5) SDN_DBG(1, it, 2 + kb);
+                    if (ptx::elect_one()) ptx::tc_commit(&empty_bar[s]);
+                    __syncwarp();
+                    if (lane == 0 && kb < 5) SDN_DBG(1, it, 2 + kb);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                ptx::tc_commit(&tfull_bar[a]);
-                SDN_DBG(1, it, 7);
+                if (ptx::elect_one()) ptx::tc_commit(&tfull_bar[a]);
+                if (lane == 0) SDN_DBG(1, it, 7);
                 a ^= 1;
                 if (a == 0) aph ^= 1;
             }

@@ -52,43 +52,72 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 // mode 6: conv3x3 dgrad     dst[ci][k]                    = W[channel][ci][8 - tap]       (Kpad = KB)
 // oscale (modes 0, 2, 5 only): per-output-channel factor folded into the packed weights
 // (eval-mode BatchNorm: w' = w * gamma / sqrt(running_var + eps)); nullptr = 1.
-__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int mode, int Co, int Ci,
-                                   int Kpad, const float* __restrict__ oscale) {
-    const int total = (mode == 2) ? Co * Kpad : ((mode == 3 || mode == 4) ? 4 * Co * Ci : 9 * Co * Ci);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        float v = 0.f;
-        if (mode == 0) {
-            const int co = i / (9 * Ci), rem = i % (9 * Ci), tap = rem / Ci, ci = rem % Ci;
+__device__ __forceinline__ float pack_value(const float* __restrict__ w, int mode, int Co, int Ci, int Kpad,
+                                            const float* __restrict__ oscale, int i) {
+    float v = 0.f;
+    if (mode == 0) {
+        const int co = i / (9 * Ci), rem = i % (9 * Ci), tap = rem / Ci, ci = rem % Ci;
+        v = w[(co * Ci + ci) * 9 + tap];
+        if (oscale != nullptr) v *= oscale[co];
+    } else if (mode == 1) {
+        const int ci = i / (9 * Co), rem = i % (9 * Co), tap = rem / Co, co = rem % Co;
+        v = w[(co * Ci + ci) * 9 + (8 - tap)];
+    } else if (mode == 2) {
+        const int co = i / Kpad, k = i % Kpad;
+        if (k < 9 * Ci) {
+            const int tap = k / Ci, ci = k % Ci;
             v = w[(co * Ci + ci) * 9 + tap];
             if (oscale != nullptr) v *= oscale[co];
-        } else if (mode == 1) {
-            const int ci = i / (9 * Co), rem = i % (9 * Co), tap = rem / Co, co = rem % Co;
-            v = w[(co * Ci + ci) * 9 + (8 - tap)];
-        } else if (mode == 2) {
-            const int co = i / Kpad, k = i % Kpad;
-            if (k < 9 * Ci) {
-                const int tap = k / Ci, ci = k % Ci;
-                v = w[(co * Ci + ci) * 9 + tap];
-                if (oscale != nullptr) v *= oscale[co];
-            }
-        } else if (mode == 5 || mode == 6) {
-            const int KB = Kpad;
-            const int kin = mode == 5 ? Ci : Co;      // channels on the K side
-            const int row = i / (9 * kin), k = i % (9 * kin);
-            const int blocks = kin / KB;
-            const int c = k % KB, dy = (k / KB) % 3, unit = k / (3 * KB);
-            const int dx = unit / blocks, cb = unit % blocks;
-            const int chan = cb * KB + c, tap = dy * 3 + dx;
-            v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
-            if (mode == 5 && oscale != nullptr) v *= oscale[row];
-        } else if (mode == 3) {
-            const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
-            v = w[(ci * Co + co) * 4 + q];
-        } else {
-            const int ci = i / (4 * Co), rem = i % (4 * Co), q = rem / Co, co = rem % Co;
-            v = w[(ci * Co + co) * 4 + q];
         }
-        dst[i] = __float2bfloat16_rn(v);
+    } else if (mode == 5 || mode == 6) {
+        const int KB = Kpad;
+        const int kin = mode == 5 ? Ci : Co;      // channels on the K side
+        const int row = i / (9 * kin), k = i % (9 * kin);
+        const int blocks = kin / KB;
+        const int c = k % KB, dy = (k / KB) % 3, unit = k / (3 * KB);
+        const int dx = unit / blocks, cb = unit % blocks;
+        const int chan = cb * KB + c, tap = dy * 3 + dx;
+        v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
+        if (mode == 5 && oscale != nullptr) v *= oscale[row];
+    } else if (mode == 3) {
+        const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
+        v = w[(ci * Co + co) * 4 + q];
+    } else if (mode == 4) {
+        const int ci = i / (4 * Co), rem = i % (4 * Co), q = rem / Co, co = rem % Co;
+        v = w[(ci * Co + co) * 4 + q];
+    } else {  // mode 7: bias replicated over the 4 convT quadrants (fp32 destination)
+        v = w[i % Co];
+    }
+    return v;
+}
+
+// Every layer's packing in ONE launch (the table rides in the kernel parameters).
+struct PackEntry {
+    const float* w;
+    void* dst;
+    const float* oscale;
+    int mode, Co, Ci, Kpad;
+    int start;  // first flat index of this entry
+};
+struct PackTable {
+    PackEntry e[52];
+    int n;
+    int total;
+};
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackTable t) {
+    __shared__ int starts[53];
+    if (threadIdx.x <= t.n) starts[threadIdx.x] = threadIdx.x < t.n ? t.e[threadIdx.x].start : t.total;
+    __syncthreads();
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.total; idx += gridDim.x * blockDim.x) {
+        int lo = 0, hi = t.n - 1;
+        while (lo < hi) {  // last entry with start <= idx
+            const int mid = (lo + hi + 1) >> 1;
+            if (starts[mid] <= idx) lo = mid; else hi = mid - 1;
+        }
+        const PackEntry& e = t.e[lo];
+        const float v = pack_value(e.w, e.mode, e.Co, e.Ci, e.Kpad, e.oscale, idx - e.start);
+        if (e.mode == 7) reinterpret_cast<float*>(e.dst)[idx - e.start] = v;
+        else reinterpret_cast<bf16*>(e.dst)[idx - e.start] = __float2bfloat16_rn(v);
     }
 }
 
@@ -158,14 +187,21 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
                                          long long* __restrict__ num_batches, float eps, float momentum,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches != nullptr) *num_batches += 1;
+    // one warp per channel: lanes stride over the partial rows, fixed-shape butterfly -> deterministic
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c == 0 && lane == 0 && num_batches != nullptr) *num_batches += 1;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < nparts; ++i) {
+    for (int i = lane; i < nparts; i += 32) {
         s += (double)partials[(size_t)i * 2 * C + c];
         q += (double)partials[(size_t)i * 2 * C + C + c];
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane != 0) return;
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -388,13 +424,19 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nparts; ++i) {
+    for (int i = lane; i < nparts; i += 32) {
         s1 += (double)partials[(size_t)i * 2 * C + c];
         s2 += (double)partials[(size_t)i * 2 * C + C + c];
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     c1[c] = (float)(s1 / count);
     c2[c] = (float)(s2 / count);
     if (dgamma != nullptr) {

@@ -748,41 +748,39 @@ static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
     return (int)std::max(1LL, std::min(need, cap));
 }
 
-// bf16 operand cache <- fp32 parameters
+// bf16 operand cache <- fp32 parameters: one launch for every layer
 static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
-    const bool fold = !training;   // eval: BatchNorm scale folded into the forward weights
     ProfScope ps(c, st, "pack_weights", 0, 0.0, 7763938.0 * (4 + 2) * (training ? 2 : 1));
+    const bool fold = !training;   // eval: BatchNorm scale folded into the forward weights
+    PackTable t;
+    t.n = 0;
+    t.total = 0;
+    auto add = [&](const float* w, void* dst, const float* oscale, int mode, int Co, int Ci, int Kpad, int count) {
+        PackEntry& e = t.e[t.n++];
+        e.w = w; e.dst = dst; e.oscale = oscale; e.mode = mode; e.Co = Co; e.Ci = Ci; e.Kpad = Kpad;
+        e.start = t.total;
+        t.total += count;
+    };
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
         const float* w = c->params[L.p_w];
         if (L.first) {
-            pack_weight_kernel<<<ew_grid(c, L.cout * 64, 256), 256, 0, st>>>(w, L.wf, 2, L.cout, L.cin, 64,
-                                                                            fold ? L.scale : nullptr);
-            ++c->launches;
+            add(w, L.wf, fold ? L.scale : nullptr, 2, L.cout, L.cin, 64, L.cout * 64);
         } else {
             const int n = 9 * L.cin * L.cout;
-            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wf, L.fprop.halo ? 5 : 0, L.cout, L.cin,
-                                                                   L.fprop.swa / 2, fold ? L.scale : nullptr);
-            ++c->launches;
-            if (training) {
-                pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(w, L.wd, L.dgrad.halo ? 6 : 1, L.cout, L.cin,
-                                                                       L.dgrad.swa / 2, nullptr);
-                ++c->launches;
-            }
+            add(w, L.wf, fold ? L.scale : nullptr, L.fprop.halo ? 5 : 0, L.cout, L.cin, L.fprop.swa / 2, n);
+            if (training) add(w, L.wd, nullptr, L.dgrad.halo ? 6 : 1, L.cout, L.cin, L.dgrad.swa / 2, n);
         }
     }
     for (int k = 0; k < 4; ++k) {
         UpL& U = c->up[k];
         const int n = 4 * U.cin * U.cout;
-        pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wf, 3, U.cout, U.cin, 0, nullptr);
-        ++c->launches;
-        if (training) {
-            pack_weight_kernel<<<ew_grid(c, n, 256), 256, 0, st>>>(c->params[U.p_w], U.wd, 4, U.cout, U.cin, 0, nullptr);
-            ++c->launches;
-        }
-        tile_bias_kernel<<<1, 256, 0, st>>>(c->params[U.p_b], U.bias4, U.cout, 4);
-        ++c->launches;
+        add(c->params[U.p_w], U.wf, nullptr, 3, U.cout, U.cin, 0, n);
+        if (training) add(c->params[U.p_w], U.wd, nullptr, 4, U.cout, U.cin, 0, n);
+        add(c->params[U.p_b], U.bias4, nullptr, 7, U.cout, 0, 0, 4 * U.cout);
     }
+    pack_all_kernel<<<c->num_sms * 4, 256, 0, st>>>(t);
+    ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -870,7 +868,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
                      (double)B * L.y.H * L.y.W * L.cout * 2 * (L.pooled_out ? 2.25 : 2.0));
         if (training) {
             const double count = (double)B * L.y.H * L.y.W;
-            bn_finalize_train_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(
+            bn_finalize_train_kernel<<<(L.cout * 32 + 255) / 256, 256, 0, st>>>(
                 c->stats_partials, op.grid, L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
                 c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd);
             ++c->launches;
@@ -905,7 +903,7 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
         bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, L.scale, L.shift, L.mean, L.rstd,
                                                           c->bwd_partials, B, H, W, C);
     ++c->launches;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(c->bwd_partials, grid, C, count, L.c1, L.c2,
+    bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(c->bwd_partials, grid, C, count, L.c1, L.c2,
                                                             c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate);
     ++c->launches;
     const int agrid = ew_grid(c, items, 256);

@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     const int my_tiles = (int)blockIdx.x < ptiles ? (ptiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
-        if (lane == 0) {
-            ptx::prefetch_tmap(&p.a_maps[variant]);
-            ptx::prefetch_tmap(&p.b_maps[0]);
-            ptx::prefetch_tmap(&p.b_maps[1]);
+        {   // converged warp; one elected lane issues the arrive + TMA instructions
+            if (lane == 0) {
+                ptx::prefetch_tmap(&p.a_maps[variant]);
+                ptx::prefetch_tmap(&p.b_maps[0]);
+                ptx::prefetch_tmap(&p.b_maps[1]);
+            }
             int s = 0;
             uint32_t ph = 0;
             const uint32_t tx_bytes = p.a_atoms * a_tile_bytes + nunits * (b_rows * SWB);
@@ -123,23 +125,28 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * stage_bytes;
                 uint8_t* b_dst = a_dst + p.a_atoms * a_tile_bytes;
-                ptx::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-                for (int i = 0; i < p.a_atoms; ++i)
-                    ptx::tma_load_4d(a_dst + i * a_tile_bytes, &p.a_maps[variant], &full_bar[s],
-                                     m_tile * 128 + i * 64, x0, y0, n0);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                    for (int i = 0; i < p.a_atoms; ++i)
+                        ptx::tma_load_4d(a_dst + i * a_tile_bytes, &p.a_maps[variant], &full_bar[s],
+                                         m_tile * 128 + i * 64, x0, y0, n0);
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    if (g < nunits)
-                        ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[u_src[g]], &full_bar[s], u_c0[g],
-                                         x0 + u_dx[g], y0 - p.halo, n0);
+                    for (int g = 0; g < 8; ++g)
+                        if (g < nunits)
+                            ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[u_src[g]], &full_bar[s], u_c0[g],
+                                             x0 + u_dx[g], y0 - p.halo, n0);
+                }
+                __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the loop converged (descriptor math stays in uniform registers);
+            // only the tcgen05 instructions are issued by one elected lane
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t idesc = ptx::make_idesc_bf16(128, ndy * CA, 1, 1);
+            // one dY atom -> M = 64 (half the shared-memory operand reads of an aliased M = 128)
+            const uint32_t idesc = ptx::make_idesc_bf16(p.a_atoms == 2 ? 128 : 64, ndy * CA, 1, 1);
             const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
             const uint32_t b_lbo = uint32_t(p.TW * SWB);  // one image row of the halo box = one vertical tap
             // descriptors of stage 0; later stages / k-steps / units only add to the 14-bit address field
@@ -159,19 +166,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                     const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
                     const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
                     const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-                    for (int g = 0; g < nunits; ++g)
-                        ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
+                    for (int g = 0; g < nunits; ++g) {
+                        if (ptx::elect_one())
+                            ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
+                    }
                 }
-                ptx::tc_commit(&empty_bar[s]);
+                if (ptx::elect_one()) ptx::tc_commit(&empty_bar[s]);
+                __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
-            ptx::tc_commit(tfull_bar);
+            if (ptx::elect_one()) ptx::tc_commit(tfull_bar);
         }
     } else {
         const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;
+        // M = 128: accumulator row r lives in TMEM lane r.  M = 64 (cta_group::1): row r lives in lane
+        // 32 * (r / 16) + r % 16, i.e. each warp's lane quarter holds 16 rows in its first 16 lanes.
+        const bool m64 = p.a_atoms == 1;
+        const int r = m64 ? quarter * 16 + lane : quarter * 32 + lane;
         const int co = m_tile * 128 + r;
-        const bool row_ok = (r < p.a_atoms * 64) && (co < p.cout);
+        const bool row_ok = (m64 ? lane < 16 : true) && (co < p.cout);
         if (my_tiles > 0) {
             ptx::mbar_wait(tfull_bar, 0);
             ptx::tc_fence_after();
