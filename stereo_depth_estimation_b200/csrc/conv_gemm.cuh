@@ -61,11 +61,19 @@ struct alignas(64) ConvGemmParams {
     float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS
     long long* dbg;         // optional: block 0 records clock64() per role / tile / event (timing forensics)
 };
+// Timing forensics (clock64 stamps per role / tile, ablation flags) compile in only with
+// -DSDN_FORENSICS: the tcgen05 issue path is sensitive to extra predicates.
+#ifdef SDN_FORENSICS
 #define SDN_DBG(role, tile, ev)                                                              \
     do {                                                                                     \
         if (p.dbg != nullptr && blockIdx.x == 0 && (tile) < 16)                              \
             p.dbg[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                            \
     } while (0)
+#define SDN_ABLATE(flag) ((p.flags & (flag)) != 0)
+#else
+#define SDN_DBG(role, tile, ev) do { } while (0)
+#define SDN_ABLATE(flag) false
+#endif
 
 template <int SWA, int BLOCK_N>
 struct CgCfg {
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                         uint8_t* b_dst = a_dst + a_bytes;
                         if (HALO) {
                             const uint32_t a_box = uint32_t(p.TW * (p.TH + 2) * SWA);
-                            const bool noa = (p.flags & CG_DBG_NOLOADA) != 0;
+                            const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
                             if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                             if (ptx::elect_one()) {
                                 if (sub == 0)
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
                     const uint32_t st_addr = ptx::smem_u32(stage_base + s * stage_bytes);
-                    if (p.flags & CG_DBG_NOMMA) {
+                    if (SDN_ABLATE(CG_DBG_NOMMA)) {
                     } else if (HALO) {
                         for (int j = 0; j < ups; ++j) {
                             const uint32_t a_addr = st_addr + j * unit_bytes;
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         const int te = threadIdx.x - 64;     // 0..127
         const int quarter = warp & 3;        // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;   // tile row == pixel index in the box
-        const bool do_stats = (p.flags & CG_STATS) != 0 && !(p.flags & CG_DBG_NOSTATS);
+        const bool do_stats = (p.flags & CG_STATS) != 0 && !SDN_ABLATE(CG_DBG_NOSTATS);
         const bool do_relu = (p.flags & CG_RELU) != 0;
         int a = 0;
         uint32_t aph = 0;
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             ptx::tc_fence_after();
             if (te == 0) SDN_DBG(2, dbg_tile, 2);
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BLOCK_N;
-            if (!(p.flags & CG_DBG_NOEPI))
+            if (!SDN_ABLATE(CG_DBG_NOEPI))
 #pragma unroll
             for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
                 uint32_t v[32];
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             ptx::named_bar_sync(1, 128);
             if (te == 0) SDN_DBG(2, dbg_tile, 4);
 
-            if (te == 0 && !(p.flags & CG_DBG_NOSTORE)) {
+            if (te == 0 && !SDN_ABLATE(CG_DBG_NOSTORE)) {
                 int dmap = 0, nrem = n_tile;   // n_tile / n_tiles_per_dmap without a division (<= 4 maps)
                 while (nrem >= dmap_div) { nrem -= dmap_div; ++dmap; }
                 const int cbase = nrem * BLOCK_N;

@@ -133,33 +133,37 @@ __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict_
 // the 3 x Cin input row segments are staged in shared memory with coalesced
 // loads, then every thread emits 16-byte chunks (8 consecutive k of one pixel),
 // so 8 consecutive threads write one pixel's 128 contiguous bytes.
-constexpr int IM2COL_PX = 128;
+constexpr int IM2COL_PX = 160;   // pixels per block in x
+constexpr int IM2COL_ROWS = 4;   // output rows per block (they share the staged input rows)
 constexpr int IM2COL_MAXC = 8;
 
 template <int Cin>
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
                                                            int H, int W) {
-    __shared__ float tile[IM2COL_MAXC * 3][IM2COL_PX + 2];
-    const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
-    const int xb = blockIdx.x % xblocks;
-    const int yh = (blockIdx.x / xblocks) % H;
-    const int n = blockIdx.x / (xblocks * H);
-    const int x0 = xb * IM2COL_PX;
-    constexpr int K = 9 * Cin;
+    __shared__ float tile[Cin * (IM2COL_ROWS + 2)][IM2COL_PX + 2];
     static_assert(Cin <= IM2COL_MAXC, "first-layer channel count");
-    for (int i = threadIdx.x; i < Cin * 3 * (IM2COL_PX + 2); i += blockDim.x) {
+    constexpr int K = 9 * Cin;
+    constexpr int TR = IM2COL_ROWS + 2;
+    const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
+    const int yblocks = (H + IM2COL_ROWS - 1) / IM2COL_ROWS;
+    const int xb = blockIdx.x % xblocks;
+    const int yb = (blockIdx.x / xblocks) % yblocks;
+    const int n = blockIdx.x / (xblocks * yblocks);
+    const int x0 = xb * IM2COL_PX, y0 = yb * IM2COL_ROWS;
+    for (int i = threadIdx.x; i < Cin * TR * (IM2COL_PX + 2); i += blockDim.x) {
         const int col = i % (IM2COL_PX + 2);
-        const int row = i / (IM2COL_PX + 2);  // c * 3 + dy
-        const int c = row / 3, dy = row % 3;
-        const int yy = yh + dy - 1, xx = x0 + col - 1;
+        const int row = i / (IM2COL_PX + 2);  // c * TR + r
+        const int c = row / TR, r = row % TR;
+        const int yy = y0 + r - 1, xx = x0 + col - 1;
         float v = 0.f;
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * Cin + c) * H + yy) * W + xx);
         tile[row][col] = v;
     }
     __syncthreads();
     const int npx = min(IM2COL_PX, W - x0);
-    for (int i = threadIdx.x; i < npx * 8; i += blockDim.x) {
-        const int g = i & 7, px = i >> 3;
+    const int nrows = min(IM2COL_ROWS, H - y0);
+    for (int i = threadIdx.x; i < nrows * npx * 8; i += blockDim.x) {
+        const int g = i & 7, px = (i >> 3) % npx, ry = (i >> 3) / npx;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -167,11 +171,11 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
             float v = 0.f;
             if (k < K) {
                 const int tap = k / Cin, c = k % Cin;
-                v = tile[c * 3 + tap / 3][px + tap % 3];
+                v = tile[c * TR + ry + tap / 3][px + tap % 3];
             }
             f[j] = v;
         }
-        const size_t pix = ((size_t)n * H + yh) * W + x0 + px;
+        const size_t pix = ((size_t)n * H + y0 + ry) * W + x0 + px;
         *reinterpret_cast<uint4*>(out + pix * 64 + g * 8) = pack8(f);
     }
 }

@@ -538,7 +538,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     p.total_units = (p.halo ? 3 : 1) * p.atoms_per_tap;
     const int a_bytes = p.a_atoms * p.kpix * 128;
     const int b_tile_bytes = (b_rows * op.swb + 1023) & ~1023;
-    int umax = std::min(p.total_units, 512 / (ndy * CA));
+    int umax = std::min(p.total_units, (p.halo ? 512 : 256) / (ndy * CA));   // plain units share one N <= 256 MMA
     while (umax > 1 && 3 * (a_bytes + umax * b_tile_bytes) + 2048 > 200 * 1024) --umax;  // keep >= 3 stages
     p.unit_groups = (p.total_units + umax - 1) / umax;
     p.U = (p.total_units + p.unit_groups - 1) / p.unit_groups;
@@ -821,7 +821,8 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     {
         const double px = (double)B * H * W;
         ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + 64 * 2));
-        im2col_first_kernel<6><<<B * H * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st>>>(x, c->x0.p, B, H, W);
+        im2col_first_kernel<6><<<B * ((H + IM2COL_ROWS - 1) / IM2COL_ROWS) * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st>>>(
+            x, c->x0.p, B, H, W);
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());

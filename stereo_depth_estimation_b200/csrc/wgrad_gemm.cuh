@@ -146,9 +146,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             int s = 0;
             uint32_t ph = 0;
             // one dY atom -> M = 64 (half the shared-memory operand reads of an aliased M = 128)
-            const uint32_t idesc = ptx::make_idesc_bf16(p.a_atoms == 2 ? 128 : 64, ndy * CA, 1, 1);
+            // halo: one MMA per unit (N = 3 row-shifted atoms, LBO = one image row).  plain: the units are
+            // whole tiles b_tile_bytes apart, so ONE MMA covers all of them (N = nunits * CA <= 256).
+            const bool grouped = !p.halo && nunits * CA <= 256;
+            const uint32_t idesc = ptx::make_idesc_bf16(p.a_atoms == 2 ? 128 : 64, grouped ? nunits * CA : ndy * CA, 1, 1);
             const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
-            const uint32_t b_lbo = uint32_t(p.TW * SWB);  // one image row of the halo box = one vertical tap
+            const uint32_t b_lbo = p.halo ? uint32_t(p.TW * SWB) : uint32_t(b_tile_bytes);  // halo: one image row = one vertical tap
             // descriptors of stage 0; later stages / k-steps / units only add to the 14-bit address field
             const uint32_t smem0 = ptx::smem_u32(smem);
             const uint64_t adesc0 = ptx::make_smem_desc(smem0, a_lbo, 1024, 2u);
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             const uint32_t b_unit16 = uint32_t(b_tile_bytes) >> 4;
             const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
             const uint32_t ncol = uint32_t(ndy * CA);
+            const int nmma = grouped ? 1 : nunits;
             for (int it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                     const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
                     const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
                     const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-                    for (int g = 0; g < nunits; ++g) {
+                    for (int g = 0; g < nmma; ++g) {
                         if (ptx::elect_one())
                             ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
                     }
