@@ -296,8 +296,13 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     return fail("no conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
 }
 static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
-    if (op.swb == 128) wgrad_gemm_kernel<128><<<op.grid, 192, op.smem, st>>>(op.p);
-    else wgrad_gemm_kernel<64><<<op.grid, 192, op.smem, st>>>(op.p);
+    if (op.swb == 128) {
+        if (op.p.halo) wgrad_gemm_kernel<128, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        else wgrad_gemm_kernel<128, false><<<op.grid, 192, op.smem, st>>>(op.p);
+    } else {
+        if (op.p.halo) wgrad_gemm_kernel<64, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        else wgrad_gemm_kernel<64, false><<<op.grid, 192, op.smem, st>>>(op.p);
+    }
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -310,8 +315,10 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 32, true); SDN_SMEM_ATTR(128, 64, true); SDN_SMEM_ATTR(128, 128, true);
     SDN_SMEM_ATTR(64, 32, true); SDN_SMEM_ATTR(64, 64, true);
 #undef SDN_SMEM_ATTR
-    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
 }
 

@@ -52,7 +52,7 @@ struct alignas(64) WgradParams {
     float* out;             // [a_variants][taps * cin_tot][cout] fp32, pre-zeroed
 };
 
-template <int SWB>
+template <int SWB, bool HALO>
 __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
     constexpr int CA = SWB / 2;  // channels per B atom
     constexpr uint32_t LAYOUT_B = (SWB == 128) ? 2u : 4u;
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    const int ndy = p.halo ? 3 : 1;
+    constexpr int ndy = HALO ? 3 : 1;
     const int a_tile_bytes = p.kpix * 128;
-    const int b_rows = p.halo ? (p.TH + 2) * p.TW : p.kpix;
+    const int b_rows = HALO ? (p.TH + 2) * p.TW : p.kpix;
     const int b_tile_bytes = ((b_rows * SWB) + 1023) & ~1023;
     const int stage_bytes = p.a_atoms * a_tile_bytes + p.U * b_tile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             int u_src[8], u_c0[8], u_dx[8];
             for (int g = 0; g < nunits; ++g) {
                 const int u = unit0 + g;
-                const int dxi = p.halo ? u / p.atoms_per_tap : 1;
-                const int ca = p.halo ? u % p.atoms_per_tap : u;
+                const int dxi = HALO ? u / p.atoms_per_tap : 1;
+                const int ca = HALO ? u % p.atoms_per_tap : u;
                 u_src[g] = ca < p.atoms_src0 ? 0 : 1;
                 u_c0[g] = (u_src[g] == 0 ? ca : ca - p.atoms_src0) * CA;
                 u_dx[g] = dxi - 1;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                     for (int g = 0; g < 8; ++g)
                         if (g < nunits)
                             ptx::tma_load_4d(b_dst + g * b_tile_bytes, &p.b_maps[u_src[g]], &full_bar[s], u_c0[g],
-                                             x0 + u_dx[g], y0 - p.halo, n0);
+                                             x0 + u_dx[g], y0 - (HALO ? 1 : 0), n0);
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1; }
@@ -148,17 +148,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             // one dY atom -> M = 64 (half the shared-memory operand reads of an aliased M = 128)
             // halo: one MMA per unit (N = 3 row-shifted atoms, LBO = one image row).  plain: the units are
             // whole tiles b_tile_bytes apart, so ONE MMA covers all of them (N = nunits * CA <= 256).
-            const bool grouped = !p.halo && nunits * CA <= 256;
+            const bool grouped = !HALO && nunits * CA <= 256;
             const uint32_t idesc = ptx::make_idesc_bf16(p.a_atoms == 2 ? 128 : 64, grouped ? nunits * CA : ndy * CA, 1, 1);
             const uint32_t a_lbo = p.a_atoms == 2 ? uint32_t(a_tile_bytes) : 0u;
-            const uint32_t b_lbo = p.halo ? uint32_t(p.TW * SWB) : uint32_t(b_tile_bytes);  // halo: one image row = one vertical tap
+            const uint32_t b_lbo = HALO ? uint32_t(p.TW * SWB) : uint32_t(b_tile_bytes);  // halo: one image row = one vertical tap
             // descriptors of stage 0; later stages / k-steps / units only add to the 14-bit address field
             const uint32_t smem0 = ptx::smem_u32(smem);
             const uint64_t adesc0 = ptx::make_smem_desc(smem0, a_lbo, 1024, 2u);
             const uint64_t bdesc0 = ptx::make_smem_desc(smem0 + p.a_atoms * a_tile_bytes, b_lbo, 8 * SWB, LAYOUT_B);
             const uint32_t b_unit16 = uint32_t(b_tile_bytes) >> 4;
             const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
-            const uint32_t ncol = uint32_t(ndy * CA);
+            constexpr uint32_t ncol = uint32_t(ndy * CA);
             const int nmma = grouped ? 1 : nunits;
             for (int it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait(&full_bar[s], ph);
@@ -170,8 +170,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                     const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
                     const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
                     const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-                    for (int g = 0; g < nmma; ++g) {
-                        if (ptx::elect_one())
+#pragma unroll
+                    for (int g = 0; g < (HALO ? 5 : 8); ++g) {
+                        if (g < nmma && ptx::elect_one())
                             ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
                     }
                 }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         if (my_tiles > 0) {
             ptx::mbar_wait(tfull_bar, 0);
             ptx::tc_fence_after();
-            const int taps = p.halo ? 9 : 1;
+            constexpr int taps = HALO ? 9 : 1;
             float* out = p.out + size_t(variant) * taps * p.cin_tot * p.cout;
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
             const int ncols = nunits * ndy * CA;
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                     const int g = cn0 / (ndy * CA);
                     const int dyi = (cn0 % (ndy * CA)) / CA;
                     const int u = unit0 + g;
-                    const int dxi = p.halo ? u / p.atoms_per_tap : 0;
-                    const int ca = p.halo ? u % p.atoms_per_tap : u;
-                    const int tap = p.halo ? dyi * 3 + dxi : 0;
+                    const int dxi = HALO ? u / p.atoms_per_tap : 0;
+                    const int ca = HALO ? u % p.atoms_per_tap : u;
+                    const int tap = HALO ? dyi * 3 + dxi : 0;
                     const int krow0 = tap * p.cin_tot + ca * CA + (cn0 % CA);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
