@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
                     const uint32_t st_addr = ptx::smem_u32(stage_base + s * stage_bytes);
+                    const bool leader = ptx::elect_one();   // one election per stage
                     if (SDN_ABLATE(CG_DBG_NOMMA)) {
                     } else if (HALO) {
                         for (int j = 0; j < ups; ++j) {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                                 const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    if (ptx::elect_one())
+                                    if (leader)
                                         ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
                                                          (kb | j | dy | k) != 0 ? 1u : 0u);
                             }
@@ -274,12 +275,12 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k) {
                             // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-                            if (ptx::elect_one())
+                            if (leader)
                                 ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
                                                  (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if (ptx::elect_one()) ptx::tc_commit(&empty_bar[s]);
+                    if (leader) ptx::tc_commit(&empty_bar[s]);
                     __syncwarp();
                     if (lane == 0 && kb < 5) SDN_DBG(1, it, 2 + kb);
                     if (++s == stages) { s = 0; ph ^= 1; }

@@ -165,18 +165,19 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 ptx::tc_fence_after();
                 const uint64_t sa = adesc0 + uint64_t(s * stage16);
                 const uint64_t sb = bdesc0 + uint64_t(s * stage16);
+                if (ptx::elect_one()) {   // one election per stage; the elected lane issues the stage's MMAs
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
-                    const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
-                    const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
-                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                    for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
+                        const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
+                        const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
+                        const uint32_t acc = (it | k) != 0 ? 1u : 0u;
 #pragma unroll
-                    for (int g = 0; g < (HALO ? 5 : 8); ++g) {
-                        if (g < nmma && ptx::elect_one())
-                            ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
+                        for (int g = 0; g < (HALO ? 5 : 8); ++g)
+                            if (g < nmma)
+                                ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
                     }
+                    ptx::tc_commit(&empty_bar[s]);
                 }
-                if (ptx::elect_one()) ptx::tc_commit(&empty_bar[s]);
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
