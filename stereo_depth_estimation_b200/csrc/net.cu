@@ -564,7 +564,9 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     op.smem = stages * stage_bytes + 2048;
     const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
-    int split = (2 * c->num_sms + ctas_per_split - 1) / ctas_per_split;
+    static int waves = -1;
+    if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 2; }
+    int split = (waves * c->num_sms + ctas_per_split - 1) / ctas_per_split;   // one CTA per SM: 1 CTA/SM occupancy
     split = std::max(1, std::min(split, ptiles));
     op.grid = dim3(split, p.unit_groups, p.m_tiles * p.a_variants);
     return 0;
