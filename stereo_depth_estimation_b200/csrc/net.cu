@@ -1003,6 +1003,62 @@ static int backward_prologue(sdn_ctx* c, int accumulate, cudaStream_t st) {
     return 0;
 }
 
+static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B,
+                            int Hs, int Ws, const AugParams* aug, float* input, float* target, uint8_t* mask,
+                            unsigned long long* valid_count, unsigned flags, float* gray_part, float* blur_tmp,
+                            cudaStream_t st) {
+    const int H = c->H, W = c->W;
+    const int xblocks = (W + 127) / 128, yblocks = (H + PRE_ROWS - 1) / PRE_ROWS;
+    const int parts = xblocks * yblocks;
+    // SURVEY 8(d): 3 uint8 sources read + fp32 input/target + u8 mask written per sample
+    // decode+resize moves the SURVEY 8(d) bytes; the augmentation passes re-read / re-write the fp32 views
+    ProfScope* ps = new ProfScope(c, st, "pre_decode_resize", 0, 0.0,
+                                  (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
+    // shared-memory staged kernel when the source rows are 16-byte aligned and the footprint fits
+    const int max_rows = (int)std::ceil((double)PRE_ROWS * Hs / H) + 3;
+    const int row_bytes = (((int)std::ceil(128.0 * Ws / W) + 3) * 3 + 47) & ~15;
+    const size_t pre_smem = (size_t)3 * max_rows * row_bytes;
+    const bool aligned = ((Ws * 3) % 16 == 0) && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)disparity) % 16 == 0);
+    const bool staged = aligned && pre_smem <= 200 * 1024 && !(flags & SDN_PREPROCESS_DIRECT);
+    if (staged) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        if (flags & SDN_RESIZE_FOURTERM)
+            decode_resize_smem_kernel<true><<<dim3(parts, B), 256, pre_smem, st>>>(
+                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
+                aug ? gray_part : nullptr, parts, max_rows, row_bytes);
+        else
+            decode_resize_smem_kernel<false><<<dim3(parts, B), 256, pre_smem, st>>>(
+                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
+                aug ? gray_part : nullptr, parts, max_rows, row_bytes);
+    } else if (flags & SDN_RESIZE_FOURTERM)
+        decode_resize_kernel<true><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
+                                                                   target, mask, valid_count, aug,
+                                                                   aug ? gray_part : nullptr, parts);
+    else
+        decode_resize_kernel<false><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
+                                                                    target, mask, valid_count, aug,
+                                                                    aug ? gray_part : nullptr, parts);
+    ++c->launches;
+    delete ps;
+    if (aug != nullptr) {
+        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
+        augment_point_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(input, B, H, W, aug, gray_part, parts,
+                                                                              blur_tmp);
+        ++c->launches;
+        blur_noise_kernel<5><<<dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st>>>(input, B, H, W, aug,
+                                                                                              blur_tmp);
+        ++c->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1180,56 +1236,22 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     if (Hs < 1 || Ws < 1) return fail("sdn_preprocess: bad source size %dx%d", Hs, Ws);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaSetDevice(c->device));
-    const int H = c->H, W = c->W;
-    const int xblocks = (W + 127) / 128, yblocks = (H + PRE_ROWS - 1) / PRE_ROWS;
-    const int parts = xblocks * yblocks;
     if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
-    const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
-    // SURVEY 8(d): 3 uint8 sources read + fp32 input/target + u8 mask written per sample
-    // decode+resize moves the SURVEY 8(d) bytes; the augmentation passes re-read / re-write the fp32 views
-    ProfScope* ps = new ProfScope(c, st, "pre_decode_resize", 0, 0.0,
-                                  (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
-    // shared-memory staged kernel when the source rows are 16-byte aligned and the footprint fits
-    const int max_rows = (int)std::ceil((double)PRE_ROWS * Hs / H) + 3;
-    const int row_bytes = (((int)std::ceil(128.0 * Ws / W) + 3) * 3 + 47) & ~15;
-    const size_t pre_smem = (size_t)3 * max_rows * row_bytes;
-    const bool aligned = ((Ws * 3) % 16 == 0) && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)disparity) % 16 == 0);
-    const bool staged = aligned && pre_smem <= 200 * 1024 && !(flags & SDN_PREPROCESS_DIRECT);
-    if (staged) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
-        if (flags & SDN_RESIZE_FOURTERM)
-            decode_resize_smem_kernel<true><<<dim3(parts, B), 256, pre_smem, st>>>(
-                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
-                aug ? c->gray_part : nullptr, parts, max_rows, row_bytes);
-        else
-            decode_resize_smem_kernel<false><<<dim3(parts, B), 256, pre_smem, st>>>(
-                left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
-                aug ? c->gray_part : nullptr, parts, max_rows, row_bytes);
-    } else if (flags & SDN_RESIZE_FOURTERM)
-        decode_resize_kernel<true><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
-                                                                   target, mask, valid_count, aug,
-                                                                   aug ? c->gray_part : nullptr, parts);
-    else
-        decode_resize_kernel<false><<<dim3(parts, B), 128, 0, st>>>(left, right, disparity, B, Hs, Ws, H, W, input,
-                                                                    target, mask, valid_count, aug,
-                                                                    aug ? c->gray_part : nullptr, parts);
-    ++c->launches;
-    delete ps;
-    if (aug != nullptr) {
-        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
-        augment_point_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(input, B, H, W, aug, c->gray_part, parts,
-                                                                              c->blur_tmp);
-        ++c->launches;
-        blur_noise_kernel<5><<<dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st>>>(input, B, H, W, aug,
-                                                                                              c->blur_tmp);
-        ++c->launches;
+    const AugParams* aug_all = reinterpret_cast<const AugParams*>(aug_dev);
+    // With augmentation on, samples go through in chunks whose fp32 views stay L2-resident between the
+    // decode/resize pass and the in-place augmentation pass, so DRAM sees each byte about once.
+    static int chunk_cfg = -1;
+    if (chunk_cfg < 0) { const char* e = getenv("SDN_PRE_CHUNK"); chunk_cfg = e ? atoi(e) : 16; }
+    const int chunk = (aug_all != nullptr && chunk_cfg > 0) ? chunk_cfg : B;
+    const size_t src_img = (size_t)Hs * Ws * 3, plane = (size_t)c->H * c->W;
+    const int parts = ((c->W + 127) / 128) * ((c->H + PRE_ROWS - 1) / PRE_ROWS);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        SDN_OK(preprocess_chunk(c, left + b0 * src_img, right + b0 * src_img, disparity + b0 * src_img, nb, Hs, Ws,
+                                aug_all ? aug_all + 2 * b0 : nullptr, input + (size_t)b0 * 6 * plane,
+                                target + (size_t)b0 * plane, mask + (size_t)b0 * plane, valid_count, flags,
+                                c->gray_part + (size_t)2 * b0 * parts, c->blur_tmp + (size_t)2 * b0 * 3 * plane, st));
     }
-    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -106,8 +106,15 @@ class AugmentSampler:
         if self.noise_std_max > 0:
             rec["noise_std"] = self.rng.uniform(0.0, self.noise_std_max, n)
         rec["noise_seed"] = self.rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32)
-        t = torch.from_numpy(rec.view(np.uint8).copy())
-        return t.pin_memory() if torch.cuda.is_available() else t
+        raw = torch.from_numpy(rec.view(np.uint8))
+        if not torch.cuda.is_available():
+            return raw.clone()
+        # a small ring of pinned staging buffers (cudaHostAlloc per call is slow; the H2D copy is async)
+        ring = self.__dict__.setdefault("_pinned_ring", {})
+        bufs = ring.setdefault(raw.numel(), [torch.empty(raw.numel(), dtype=torch.uint8).pin_memory() for _ in range(4)])
+        slot = self.__dict__["_ring_pos"] = (self.__dict__.get("_ring_pos", -1) + 1) % 4
+        bufs[slot].copy_(raw)
+        return bufs[slot]
 
 
 AUG_DTYPE = np.dtype([("brightness", "<f4"), ("contrast", "<f4"), ("saturation", "<f4"), ("hue", "<f4"),
