@@ -313,6 +313,16 @@ def run_b200(args):
         achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         roof = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if any
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_wgrad_b256_summary.json")) as f:
+            cap = json.load(f)
+        if dname in ("conv_wgrad", "convT_wgrad") and b_local == 256:
+            roof["traffic"] = cap["dram_bytes_per_launch_avg"]
+            roof["traffic_source"] = "profiles/r1_ncu_wgrad_b256_summary.json (ncu --set full, dram__bytes_read+write per launch)"
+            roof["algorithmic_bytes_per_launch"] = d["bytes"] / max(d["calls"], 1)
+    except Exception:
+        pass
     roof["share_of_step"] = d["ms"] / total_prof_ms if total_prof_ms > 0 else None
     roof["launches_per_step"] = d["calls"]
     families = {k: {"ms_per_step": v["ms"],
