@@ -297,10 +297,12 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
 }
 static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
     if (op.swb == 128) {
-        if (op.p.halo) wgrad_gemm_kernel<128, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        if (op.p.tr) wgrad_gemm_kernel<128, true, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        else if (op.p.halo) wgrad_gemm_kernel<128, true><<<op.grid, 192, op.smem, st>>>(op.p);
         else wgrad_gemm_kernel<128, false><<<op.grid, 192, op.smem, st>>>(op.p);
     } else {
-        if (op.p.halo) wgrad_gemm_kernel<64, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        if (op.p.tr) wgrad_gemm_kernel<64, true, true><<<op.grid, 192, op.smem, st>>>(op.p);
+        else if (op.p.halo) wgrad_gemm_kernel<64, true><<<op.grid, 192, op.smem, st>>>(op.p);
         else wgrad_gemm_kernel<64, false><<<op.grid, 192, op.smem, st>>>(op.p);
     }
     ++c->launches;
@@ -319,6 +321,8 @@ static int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<128, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<64, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
 }
 
@@ -527,9 +531,15 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     p.a_variants = (int)avariants.size();
     p.a_atoms = cout >= 128 ? 2 : 1;
     p.m_tiles = (cout + 127) / 128;
+    static int tr_on = -1;
+    if (tr_on < 0) { const char* e = getenv("SDN_WGRAD_TR"); tr_on = e ? atoi(e) : 1; }
+    // measured: the swapped roles win when a unit is 64 channels wide or when there are >= 6 units
+    // (two sources); 3 units of 32 channels are issue-bound either way and stay in the plain layout
+    p.tr = (tr_on && p.halo && (cout == 32 || cout == 64) && (CA == 64 || 3 * (cin_tot / CA) >= 6)) ? 1 : 0;
     for (size_t i = 0; i < avariants.size(); ++i) {
         const SrcView& v = avariants[i];
-        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, 64, t.TW, t.TH, t.TN, 128));
+        if (p.tr) SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, cout, t.TW, t.TH, t.TN, cout * 2));
+        else SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, 64, t.TW, t.TH, t.TN, 128));
     }
     for (size_t i = avariants.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
     const int b_rows = p.halo ? (t.TH + 2) * t.TW : p.kpix;
@@ -543,15 +553,17 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     p.atoms_src0 = bsrc[0].C / CA;
     const int ndy = p.halo ? 3 : 1;
     p.total_units = (p.halo ? 3 : 1) * p.atoms_per_tap;
-    const int a_bytes = p.a_atoms * p.kpix * 128;
+    const int a_bytes = p.tr ? p.kpix * cout * 2 : p.a_atoms * p.kpix * 128;
     const int b_tile_bytes = (b_rows * op.swb + 1023) & ~1023;
-    int umax = std::min(p.total_units, (p.halo ? 512 : 256) / (ndy * CA));   // plain units share one N <= 256 MMA
+    const int cols_per_unit = p.tr ? cout * (CA == 64 ? 2 : 1) : ndy * CA;
+    int umax = std::min(p.total_units, (p.halo ? 512 : 256) / cols_per_unit);   // plain units share one N <= 256 MMA
+    umax = std::min(umax, 8);
     while (umax > 1 && 3 * (a_bytes + umax * b_tile_bytes) + 2048 > 200 * 1024) --umax;  // keep >= 3 stages
     p.unit_groups = (p.total_units + umax - 1) / umax;
     p.U = (p.total_units + p.unit_groups - 1) / p.unit_groups;
     p.unit_groups = (p.total_units + p.U - 1) / p.U;
     int cols = 32;
-    while (cols < p.U * ndy * CA) cols *= 2;
+    while (cols < p.U * cols_per_unit) cols *= 2;
     p.tmem_cols = cols;
     p.cout = cout;
     p.cin_tot = cin_tot;

@@ -50,9 +50,15 @@ struct alignas(64) WgradParams {
     int cin_tot;
     int k_rows_valid;       // rows of the workspace that exist
     float* out;             // [a_variants][taps * cin_tot][cout] fp32, pre-zeroed
+    int tr;                 // transposed roles (Cout <= 64, 3x3): M = (vertical tap, ci) rows of a unit, N = co
 };
 
-template <int SWB, bool HALO>
+// TR (Cout <= 64, 3x3 only): the roles are swapped.  The MMA's M side is one unit's halo tile - its three
+// row-shifted vertical taps are M-atoms LBO = TW rows apart, M = 128 = 4 x 32 channels (the 4th atom is
+// garbage and ignored) or 2 x 64 (+ one M = 64 MMA for the third tap) - and the N side is dY with
+// N = Cout.  A level-1 layer then issues M=128,N=32 MMAs (16 pipe cycles) instead of M=64,N=96 ones
+// that the pipe charges as M=128 (48 cycles) with 3/4 of the rows wasted.
+template <int SWB, bool HALO, bool TR = false>
 __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
     constexpr int CA = SWB / 2;  // channels per B atom
     constexpr uint32_t LAYOUT_B = (SWB == 128) ? 2u : 4u;
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     constexpr int ndy = HALO ? 3 : 1;
-    const int a_tile_bytes = p.kpix * 128;
+    const int a_tile_bytes = TR ? p.kpix * p.cout * 2 : p.kpix * 128;   // TR: dY box is exactly Cout wide
     const int b_rows = HALO ? (p.TH + 2) * p.TW : p.kpix;
     const int b_tile_bytes = ((b_rows * SWB) + 1023) & ~1023;
     const int stage_bytes = p.a_atoms * a_tile_bytes + p.U * b_tile_bytes;
@@ -159,12 +165,47 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             const uint32_t b_unit16 = uint32_t(b_tile_bytes) >> 4;
             const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
             constexpr uint32_t ncol = uint32_t(ndy * CA);
+            const uint32_t tr_idesc128 = ptx::make_idesc_bf16(128, TR ? p.cout : 16, 1, 1);
+            const uint32_t tr_idesc64 = ptx::make_idesc_bf16(64, TR ? p.cout : 16, 1, 1);
+            const uint32_t tr_cout = uint32_t(p.cout);
+            const uint32_t tr_dy_row = uint32_t(p.cout * 2);                      // dY atom row: 64 B or 128 B
+            const uint64_t tr_ydesc0 = ptx::make_smem_desc(smem0, 0, 8 * tr_dy_row, p.cout == 64 ? 2u : 4u);
+            const uint64_t tr_xdesc0 = ptx::make_smem_desc(smem0 + a_tile_bytes, uint32_t(p.TW * SWB), 8 * SWB, LAYOUT_B);
+            const uint32_t tr_ystep16 = (16 * tr_dy_row) >> 4;
+            const uint32_t tr_dy2_16 = uint32_t(2 * p.TW * SWB) >> 4;
             const int nmma = grouped ? 1 : nunits;
             for (int it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
                 const uint64_t sa = adesc0 + uint64_t(s * stage16);
                 const uint64_t sb = bdesc0 + uint64_t(s * stage16);
+                if (TR) {
+                    if (ptx::elect_one()) {
+                        // stage-0 descriptors + (stage, k-step, unit) offsets in the 14-bit address field
+                        const uint64_t ys = tr_ydesc0 + uint64_t(s * stage16);
+                        const uint64_t xs = tr_xdesc0 + uint64_t(s * stage16);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ydesc = ys + uint64_t(k * tr_ystep16);
+                            const uint64_t xk = xs + uint64_t(k * ((16 * SWB) >> 4));
+                            const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                if (g < nunits) {
+                                    const uint64_t xdesc = xk + uint64_t(g * b_unit16);
+                                    if (CA == 32) {
+                                        ptx::tc_mma_bf16(tmem_base + g * tr_cout, xdesc, ydesc, tr_idesc128, acc);
+                                    } else {
+                                        ptx::tc_mma_bf16(tmem_base + g * 2 * tr_cout, xdesc, ydesc, tr_idesc128, acc);
+                                        ptx::tc_mma_bf16(tmem_base + g * 2 * tr_cout + tr_cout, xdesc + uint64_t(tr_dy2_16), ydesc,
+                                                         tr_idesc64, acc);
+                                    }
+                                }
+                            }
+                        }
+                        ptx::tc_commit(&empty_bar[s]);
+                    }
+                } else
                 if (ptx::elect_one()) {   // one election per stage; the elected lane issues the stage's MMAs
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
@@ -191,7 +232,35 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         const int r = m64 ? quarter * 16 + lane : quarter * 32 + lane;
         const int co = m_tile * 128 + r;
         const bool row_ok = (m64 ? lane < 16 : true) && (co < p.cout);
-        if (my_tiles > 0) {
+        if (TR && my_tiles > 0) {
+            ptx::mbar_wait(tfull_bar, 0);
+            ptx::tc_fence_after();
+            float* out = p.out;
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+            const int rr = quarter * 32 + lane;        // accumulator row of an M = 128 MMA
+            const int halves = CA == 64 ? 2 : 1;
+            for (int g = 0; g < nunits; ++g) {
+                const int u = unit0 + g;
+                const int dxi = u / p.atoms_per_tap, ca = u % p.atoms_per_tap;
+                for (int h = 0; h < halves; ++h) {
+                    int dyi, ci;
+                    bool ok;
+                    if (h == 0) { dyi = rr / CA; ci = rr % CA; ok = dyi < 3; }
+                    else { dyi = 2; ci = quarter * 16 + lane; ok = lane < 16; }   // M = 64: 16 rows per lane quarter
+                    const int krow = (dyi * 3 + dxi) * p.cin_tot + ca * CA + ci;
+                    for (int ch = 0; ch < p.cout / 32; ++ch) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + (g * halves + h) * p.cout + ch * 32, v);
+                        ptx::tmem_ld_wait();
+                        if (ok && krow < p.k_rows_valid) {
+                            float* dst = out + size_t(krow) * p.cout + ch * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            }
+        } else if (my_tiles > 0) {
             ptx::mbar_wait(tfull_bar, 0);
             ptx::tc_fence_after();
             constexpr int taps = HALO ? 9 : 1;
