@@ -237,26 +237,32 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             ptx::tc_fence_after();
             float* out = p.out;
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
-            const int rr = quarter * 32 + lane;        // accumulator row of an M = 128 MMA
             const int halves = CA == 64 ? 2 : 1;
+            // every MMA has completed, so the pipeline stages are free: use them to transpose each warp's
+            // 32 rows x 32 columns so that one red instruction covers 32 CONSECUTIVE output channels of one
+            // workspace row (coalesced) instead of 32 different rows
+            float* tsm = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
             for (int g = 0; g < nunits; ++g) {
                 const int u = unit0 + g;
                 const int dxi = u / p.atoms_per_tap, ca = u % p.atoms_per_tap;
                 for (int h = 0; h < halves; ++h) {
-                    int dyi, ci;
-                    bool ok;
-                    if (h == 0) { dyi = rr / CA; ci = rr % CA; ok = dyi < 3; }
-                    else { dyi = 2; ci = quarter * 16 + lane; ok = lane < 16; }   // M = 64: 16 rows per lane quarter
-                    const int krow = (dyi * 3 + dxi) * p.cin_tot + ca * CA + ci;
                     for (int ch = 0; ch < p.cout / 32; ++ch) {
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(taddr + (g * halves + h) * p.cout + ch * 32, v);
                         ptx::tmem_ld_wait();
-                        if (ok && krow < p.k_rows_valid) {
-                            float* dst = out + size_t(krow) * p.cout + ch * 32;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) tsm[lane * 33 + j] = __uint_as_float(v[j]);
+                        __syncwarp();
+                        const int nrows = h == 0 ? 32 : 16;   // M = 64: 16 rows per lane quarter
+                        for (int j = 0; j < nrows; ++j) {
+                            int dyi, ci;
+                            if (h == 0) { const int rr = quarter * 32 + j; dyi = rr / CA; ci = rr % CA; }
+                            else { dyi = 2; ci = quarter * 16 + j; }
+                            const int krow = (dyi * 3 + dxi) * p.cin_tot + ca * CA + ci;
+                            if (dyi < 3 && krow < p.k_rows_valid)
+                                atomicAdd(out + size_t(krow) * p.cout + ch * 32 + lane, tsm[j * 33 + lane]);
                         }
+                        __syncwarp();
                     }
                 }
             }
