@@ -200,7 +200,9 @@ def run_b200(args):
 
     torch.manual_seed(42)
     model = StereoUNet().to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)  # train.py:578 defaults
+    from stereo_depth_estimation_b200.optim import FusedAdamW
+
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)  # train.py:578 hyper-parameters
     step = FusedStep(model, opt)
     pre = DevicePreprocessor(dev, b_local, (H, W))
     sampler = AugmentSampler(seed=rank)

@@ -117,6 +117,15 @@ int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, cons
  * Copies to a host fp32 buffer of B*H_l*W_l*C_l elements; returns the dims. */
 int sdn_debug_read(sdn_ctx* ctx, int which, int kind, float* host_out, int64_t capacity, int* dims4);
 
+/* torch.optim.AdamW.step() (train.py:343,578; lr 1e-3, betas (0.9, 0.999), eps 1e-8, decoupled weight
+ * decay) over up to 66 fp32 tensors in one launch.  step_dev: device int64 counter of applied steps
+ * (incremented here); gate_dev (nullable): device u64, 0 = skip the whole update (the reference skips the
+ * batch when no pixel is valid, train.py:331-332) - no host synchronisation is needed for that rule. */
+int sdn_adamw_step(sdn_ctx* ctx, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, int n, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, long long* step_dev, const unsigned long long* gate_dev,
+                   void* stream);
+
 /* Timing forensics (SDN_DEBUG_TRACE_LAYER=<conv layer>): clock64() stamps of the three
  * warp roles of CTA 0 for its first 16 tiles, [role][tile][event] as 384 int64. */
 int sdn_debug_trace(sdn_ctx* ctx, long long* host_out);

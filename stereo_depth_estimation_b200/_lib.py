@@ -35,6 +35,7 @@ EXPORTS = (
     "sdn_count_valid",
     "sdn_preprocess",
     "sdn_debug_read",
+    "sdn_adamw_step",
     "sdn_debug_trace",
     "sdn_profile_enable",
     "sdn_profile_dump",
@@ -100,6 +101,11 @@ def load() -> ctypes.CDLL:
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint, c_void_p]
+    lib.sdn_adamw_step.restype = c_int
+    lib.sdn_adamw_step.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                   POINTER(c_int64), c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, c_void_p,
+                                   c_void_p, c_void_p]
     lib.sdn_debug_trace.restype = c_int
     lib.sdn_debug_trace.argtypes = [c_void_p, c_void_p]
     lib.sdn_profile_enable.restype = c_int

@@ -638,6 +638,54 @@ __global__ void __launch_bounds__(256) mask_count_kernel(const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------- AdamW
+// torch.optim.AdamW (decoupled weight decay, train.py:578) over all 66 parameter tensors in ONE launch,
+// same per-element operation order as torch's _single_tensor_adamw.  `gate` (device u64, e.g. the global
+// valid-pixel count) == 0 skips the whole update on the device, which is the reference's "no valid pixel
+// -> no optimizer step" rule (train.py:331-332) without a host round trip.  step_dev counts applied steps.
+struct AdamTable {
+    float* p[66];
+    const float* g[66];
+    float* m[66];
+    float* v[66];
+    int start[67];
+    int n;
+};
+__global__ void adamw_step_count_kernel(long long* step_dev, const unsigned long long* gate) {
+    if (gate == nullptr || *gate != 0ull) *step_dev += 1;
+}
+__global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ AdamTable t, double lr, double beta1,
+                                                        double beta2, float one_minus_b1, float one_minus_b2,
+                                                        float eps, float decay,
+                                                        const long long* __restrict__ step_dev,
+                                                        const unsigned long long* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0ull) return;
+    __shared__ int starts[67];
+    if (threadIdx.x <= t.n) starts[threadIdx.x] = t.start[threadIdx.x];
+    __syncthreads();
+    const double step = (double)(*step_dev);
+    const float b2f = (float)beta2;
+    const float step_size = (float)(lr / (1.0 - pow(beta1, step)));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+    const int total = starts[t.n];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int lo = 0, hi = t.n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (starts[mid] <= idx) lo = mid; else hi = mid - 1;
+        }
+        const int i = idx - starts[lo];
+        const float g = t.g[lo][i];
+        float p = t.p[lo][i] * decay;
+        float m = t.m[lo][i];
+        m = m + one_minus_b1 * (g - m);                        // lerp_
+        const float v = t.v[lo][i] * b2f + one_minus_b2 * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p = p - step_size * (m / denom);
+        t.p[lo][i] = p; t.m[lo][i] = m; t.v[lo][i] = v;
+    }
+}
+
 // ------------------------------------------------------------- grad unpack
 // workspace layouts (written by wgrad_gemm_kernel) -> torch parameter layouts.
 // mode 0: conv3x3   ws[(tap*Ci + ci)][Co]  -> grad[Co][Ci][3][3]

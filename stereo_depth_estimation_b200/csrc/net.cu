@@ -578,7 +578,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
     static int waves = -1;
     if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 2; }
-    int split = (waves * c->num_sms + ctas_per_split - 1) / ctas_per_split;   // one CTA per SM: 1 CTA/SM occupancy
+    int split = (waves * c->num_sms) / ctas_per_split;   // never spill into a partial extra wave (1 CTA per SM)
     split = std::max(1, std::min(split, ptiles));
     op.grid = dim3(split, p.unit_groups, p.m_tiles * p.a_variants);
     return 0;
@@ -1264,6 +1264,36 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
                                 target + (size_t)b0 * plane, mask + (size_t)b0 * plane, valid_count, flags,
                                 c->gray_part + (size_t)2 * b0 * parts, c->blur_tmp + (size_t)2 * b0 * 3 * plane, st));
     }
+    return 0;
+}
+
+int sdn_adamw_step(sdn_ctx* c, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, int n, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, long long* step_dev, const unsigned long long* gate_dev,
+                   void* stream) {
+    if (c == nullptr || params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr ||
+        numel == nullptr || step_dev == nullptr)
+        return fail("sdn_adamw_step: NULL argument");
+    if (n < 1 || n > 66) return fail("sdn_adamw_step: n = %d outside [1, 66]", n);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaSetDevice(c->device));
+    AdamTable t;
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+        t.p[i] = params[i]; t.g[i] = grads[i]; t.m[i] = exp_avg[i]; t.v[i] = exp_avg_sq[i];
+        t.start[i] = (int)total;
+        total += numel[i];
+    }
+    if (total > 0x7fffffffLL) return fail("sdn_adamw_step: too many elements");
+    t.start[n] = (int)total;
+    t.n = n;
+    ProfScope ps(c, st, "adamw", 0, 0.0, (double)total * 28.0);
+    adamw_step_count_kernel<<<1, 1, 0, st>>>(step_dev, gate_dev);
+    // hyper-parameters arrive as Python doubles; derived scalars are rounded to fp32 once, like torch's scalars
+    adamw_all_kernel<<<c->num_sms * 4, 256, 0, st>>>(t, lr, beta1, beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                     (float)eps, (float)(1.0 - lr * weight_decay), step_dev, gate_dev);
+    c->launches += 2;
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -30,6 +30,7 @@ import torch
 
 from . import _lib
 from .model import StereoUNet
+from .optim import FusedAdamW
 
 try:  # optional: only needed when world_size > 1
     import torch.distributed as dist
@@ -99,7 +100,8 @@ class FusedStep:
         """One optimisation step on an already-assembled batch (the reference's sample
         format).  ``valid_count`` (device int64 [1]) may come from the preprocessing
         kernel; otherwise it is counted here.  Returns the (global) valid count; 0 means
-        the step was skipped like train.py:331-332."""
+        the step was skipped like train.py:331-332 (-1 with ``FusedAdamW``: the rule is applied on the
+        device and the host never learns the count)."""
         model = self.model
         lib = _lib.load()
         x = batch["input"]
@@ -141,6 +143,10 @@ class FusedStep:
         if self.world > 1 and self.overlap:
             main.wait_stream(self.comm_stream)
 
+        if isinstance(self.optimizer, FusedAdamW):
+            # the "no valid pixel -> skip the step" rule is evaluated on the device: no host sync at all
+            self.optimizer.step(gate=self.n_norm)
+            return -1
         n_global = int(self.n_norm.cpu().item())  # the step's only host sync
         if n_global > 0 and self.optimizer is not None:
             self.optimizer.step()

@@ -394,6 +394,37 @@ def test_run_epoch_tracks_oracle_curve(dev):
     assert val["mae"] == pytest.approx(oval["mae"], rel=1.5e-1)
 
 
+def test_fused_adamw_matches_torch(dev):
+    from stereo_depth_estimation_b200.optim import FusedAdamW
+
+    torch.manual_seed(3)
+    shapes = [(32, 6, 3, 3), (32,), (64, 32, 3, 3), (1,), (512, 256, 2, 2)]
+    pa = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.AdamW(pa, lr=1e-3, weight_decay=1e-4)
+    ob = FusedAdamW(pb, lr=1e-3, weight_decay=1e-4)
+    gate = torch.ones(1, dtype=torch.int64, device=dev)
+    for it in range(4):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (0.1 + it)
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step(gate=gate)
+    for a, b in zip(pa, pb):
+        assert rel(b, a) < 1e-6
+    before = [p.detach().clone() for p in pb]
+    ob.step(gate=torch.zeros(1, dtype=torch.int64, device=dev))          # gated off: nothing moves
+    assert all(torch.equal(x, y) for x, y in zip(before, pb))
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["params"] == sb["param_groups"][0]["params"]
+    for k in sa["state"]:
+        assert set(sa["state"][k]) == set(sb["state"][k])
+        assert float(sb["state"][k]["step"]) == 4.0
+        assert rel(sb["state"][k]["exp_avg_sq"], sa["state"][k]["exp_avg_sq"]) < 1e-6
+    oc = torch.optim.AdamW([p.detach().clone().requires_grad_(True) for p in pb], lr=1e-3, weight_decay=1e-4)
+    oc.load_state_dict(sb)                                               # checkpoints interchange
+
+
 def test_checkpoint_round_trip_and_compat(dev):
     from stereo_depth_estimation_b200 import StereoUNet, load_state_dict_compat
 
