@@ -99,14 +99,19 @@ int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask
  * left / right RGB and the RGB-encoded disparity, each [B,Hs,Ws,3].
  * Outputs: input fp32 [B,6,H,W], target fp32 [B,1,H,W], mask u8 [B,1,H,W],
  * *valid_count (device u64, optional) = sum(mask & isfinite(target)).
- * aug: 2*B parameter structs on the DEVICE (left, right per sample) or NULL for
- * augment=False.
+ * aug: 2*B parameter structs on the DEVICE (left, right per sample; pinned host
+ * memory with SDN_PREPROCESS_AUG_HOST) or NULL for augment=False.
  * flags: SDN_RESIZE_FOURTERM selects the other of the two fused-multiply-add
  * orderings that torch's CPU bilinear kernel is compiled with (it is the one a
  * single-threaded DataLoader worker runs on small / 3-channel images; results
  * differ by <= 1 ulp, indices and weights are identical); 0 = canonical form. */
 #define SDN_RESIZE_FOURTERM 1u
 #define SDN_PREPROCESS_DIRECT 2u /* flags: force the un-staged kernel (tests compare both) */
+/* flags: `aug` is PINNED HOST memory (cudaHostAlloc / torch pin_memory, device-readable under UVA).  A small
+ * kernel stages it into the context, so the step issues no copy-engine transfer that would queue behind
+ * the bulk host->device prefetch of the next batch.  The caller keeps the buffer unchanged until the
+ * stream has passed this call. */
+#define SDN_PREPROCESS_AUG_HOST 4u
 int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
                    unsigned long long* valid_count, unsigned flags, void* stream);

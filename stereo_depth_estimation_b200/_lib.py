@@ -10,13 +10,15 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint, c_uint8, c_uint32, c_ulonglong, c_void_p
 
-LIB_NAME = "libsdn_b200.so"
+# SDN_LIB_NAME selects an alternative in-tree build (e.g. the -DSDN_FORENSICS timing-experiment variant)
+LIB_NAME = os.environ.get("SDN_LIB_NAME", "libsdn_b200.so")
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 NUM_PARAMS = 66
 NUM_BN = 18
 NUM_STAGES = 4
 RESIZE_FOURTERM = 1
+PREPROCESS_AUG_HOST = 4
 CTX_PREPROCESS_ONLY = 1
 
 # every symbol include/sdn.h declares (tests check that the .so exports them all)

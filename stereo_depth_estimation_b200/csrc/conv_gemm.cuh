@@ -88,7 +88,11 @@ struct CgCfg {
     static constexpr int D_BYTES = 128 * BLOCK_N * 2;
     static constexpr int WPR = DCH / 2;     // 32-bit words per staging row
     static constexpr int RG = 128 / WPR;    // row groups in the stats pass
-    static constexpr int SCRATCH_BYTES = RG * BLOCK_N * 2 * 4;
+    // small-N tiles are epilogue-bound (the per-tile bookkeeping of a 128-thread epilogue is longer than
+    // their main loop): two epilogue warpgroups, one per TMEM accumulator stage, take alternate tiles
+    static constexpr int EG = BLOCK_N <= 64 ? 2 : 1;
+    static constexpr int THREADS = 64 + 128 * EG;
+    static constexpr int SCRATCH_BYTES = EG * RG * BLOCK_N * 2 * 4;
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
     static constexpr int DBUF = BLOCK_N <= 64 ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
@@ -108,8 +112,14 @@ struct CgCfg {
 // 0, TW, 2*TW - whole 8-row swizzle groups, so the shifted descriptors stay
 // canonical - and its B operand is one 3-D box holding the three taps' weight
 // blocks.  L2->SM requests per tile drop from 9*(128+N) to 3*(TW*(TH+2)+3N).
-template <int SWA, int BLOCK_N, bool HALO>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+//
+// HALO = 2 ("box9", TW == 8, resident weights): the hardware swizzle is a pure function of the
+// shared-memory ADDRESS (probed: tests/umma_shift_probe.cu), so a descriptor may start at any row
+// and step between 8-row groups by any stride.  ONE (TH+2) x (TW+2) box per (source, channel
+// block) then serves all NINE taps: tap (dy, dx) starts (dy*(TW+2) + dx) rows into the box and
+// strides (TW+2) rows between the 8-pixel image-row segments.  L2->SM rows per tile: 180 instead of 432.
+template <int SWA, int BLOCK_N, int HALO>
+__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using Cfg = CgCfg<SWA, BLOCK_N>;
     constexpr int KB = Cfg::KB;
     constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     uint8_t* stage_base = smem;
-    const bool bres = HALO && (p.flags & CG_BRES) != 0;
+    const bool bres = HALO != 0 && (p.flags & CG_BRES) != 0;
     const int a_bytes = HALO ? p.a_stage_bytes : Cfg::A_BYTES;
     const int unit_bytes = HALO ? p.a_stage_bytes + (bres ? 0 : 3 * Cfg::B_BYTES) : Cfg::STAGE_BYTES;
     const int ups = HALO ? p.ups : 1;
@@ -176,9 +186,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             uint32_t ph = 0;
             int dbg_it = 0;
             if (bres && ptx::elect_one()) {
-                // every k-block's three weight slabs, once: [unit][dy][BLOCK_N][KB]
-                ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(p.kblocks_total) * 3 * Cfg::B_BYTES);
-                for (int u = 0; u < p.kblocks_total; ++u)
+                // every k-block's weight slabs, once: [unit][dy][BLOCK_N][KB] ([unit][dy][dx].. for box9)
+                const int slabs = p.kblocks_total * (HALO == 2 ? 3 : 1);   // 3-block TMA boxes
+                ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(slabs) * 3 * Cfg::B_BYTES);
+                for (int u = 0; u < slabs; ++u)
                     ptx::tma_load_3d(b_res + u * 3 * Cfg::B_BYTES, &p.b_map, bres_bar, 0, 0, u * 3);
             }
             ptx::TileWalker tw;
@@ -194,7 +205,17 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     for (int cb = 0; cb < seg.cblocks; ++cb) {
                         uint8_t* a_dst = stage_base + s * stage_bytes + sub * unit_bytes;
                         uint8_t* b_dst = a_dst + a_bytes;
-                        if (HALO) {
+                        if (HALO == 2) {
+                            const uint32_t a_box = uint32_t((p.TW + 2) * (p.TH + 2) * SWA);
+                            const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
+                            if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                            if (ptx::elect_one()) {
+                                if (sub == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], uint32_t(ups) * (noa ? 0 : a_box));
+                                if (!noa)
+                                    ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 - 1,
+                                                     y0 - 1, n0);
+                            }
+                        } else if (HALO == 1) {
                             const uint32_t a_box = uint32_t(p.TW * (p.TH + 2) * SWA);
                             const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
                             if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
@@ -252,7 +273,24 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     const uint32_t st_addr = ptx::smem_u32(stage_base + s * stage_bytes);
                     const bool leader = ptx::elect_one();   // one election per stage
                     if (SDN_ABLATE(CG_DBG_NOMMA)) {
-                    } else if (HALO) {
+                    } else if (HALO == 2) {
+                        const uint32_t row_pitch = uint32_t(p.TW + 2) * SWA;   // box row = TW+2 pixels
+                        for (int j = 0; j < ups; ++j) {
+                            const uint32_t a_addr = st_addr + j * unit_bytes;
+                            const uint32_t b_addr = b_res_addr + (kb + j) * 9 * Cfg::B_BYTES;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t adesc = ptx::make_smem_desc(
+                                    a_addr + (tap / 3) * row_pitch + (tap % 3) * SWA, 16, row_pitch, LAYOUT_A);
+                                const uint64_t bdesc = ptx::make_smem_desc(b_addr + tap * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
+#pragma unroll
+                                for (int k = 0; k < KB / 16; ++k)
+                                    if (leader)
+                                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                         (kb | j | tap | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                    } else if (HALO == 1) {
                         for (int j = 0; j < ups; ++j) {
                             const uint32_t a_addr = st_addr + j * unit_bytes;
                             const uint32_t b_addr = bres ? b_res_addr + (kb + j) * 3 * Cfg::B_BYTES : a_addr + a_bytes;
@@ -293,12 +331,16 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         }
     } else {
         // ------------------------------------------------------------ epilogue
-        const int te = threadIdx.x - 64;     // 0..127
+        constexpr int EG = Cfg::EG;
+        const int eg = EG == 2 ? int(threadIdx.x - 64) >> 7 : 0;   // epilogue group (== its TMEM stage when EG == 2)
+        const int te = (threadIdx.x - 64) & 127;                   // 0..127 inside the group
+        const bool dbg_lead = threadIdx.x == 64;
+        (void)dbg_lead;
         const int quarter = warp & 3;        // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;   // tile row == pixel index in the box
         const bool do_stats = (p.flags & CG_STATS) != 0 && !SDN_ABLATE(CG_DBG_NOSTATS);
         const bool do_relu = (p.flags & CG_RELU) != 0;
-        int a = 0;
+        int a = eg;
         uint32_t aph = 0;
         const int rw = r % p.TW, rh = (r / p.TW) % p.TH, rn = r / (p.TW * p.TH);  // this thread's pixel in the box
         constexpr int STAT_ROWS = 128 / Cfg::RG;
@@ -314,7 +356,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         int dbg_it = 0;
         const int dmap_div = p.n_tiles_per_dmap;
         ptx::TileWalker tw;
-        for (tw.init(blockIdx.x, gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
+        for (tw.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid();
+             tw.next()) {
             const int n_tile = tw.n_tile;
             const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
 
@@ -322,20 +365,20 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             // shifted taps, so its accumulator is not zero: zero it (the TMA store
             // clips it anyway, but the BatchNorm statistics must not see it).
             const bool row_in_image = (x0 + rw < p.img_w) && (y0 + rh < p.img_h) && (n0 + rn < p.img_n);
-            uint8_t* stg = stg0 + sbuf * Cfg::D_BYTES;
+            uint8_t* stg = stg0 + (EG == 2 ? eg : sbuf) * Cfg::D_BYTES;
             const int dbg_tile = dbg_it++;
-            if (te == 0) SDN_DBG(2, dbg_tile, 0);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 0);
             // the store issued DBUF tiles ago has finished reading this staging buffer
             if (te == 0) {
-                if (Cfg::DBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                else ptx::tma_store_wait_read0();
+                if (EG == 1 && Cfg::DBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else ptx::tma_store_wait_read0();   // EG == 2: this group's previous store, a whole tile ago
             }
-            ptx::named_bar_sync(1, 128);
-            if (te == 0) SDN_DBG(2, dbg_tile, 1);
+            ptx::named_bar_sync(1 + eg, 128);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 1);
 
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
-            if (te == 0) SDN_DBG(2, dbg_tile, 2);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 2);
             const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + a * BLOCK_N;
             if (!SDN_ABLATE(CG_DBG_NOEPI))
 #pragma unroll
@@ -377,10 +420,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[a]);
-            if (te == 0) SDN_DBG(2, dbg_tile, 3);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 3);
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(1, 128);
-            if (te == 0) SDN_DBG(2, dbg_tile, 4);
+            ptx::named_bar_sync(1 + eg, 128);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 4);
 
             if (te == 0 && !SDN_ABLATE(CG_DBG_NOSTORE)) {
                 int dmap = 0, nrem = n_tile;   // n_tile / n_tiles_per_dmap without a division (<= 4 maps)
@@ -392,6 +435,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                                       n0);
                 ptx::tma_store_commit();
             }
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 6);
             if (do_stats) {
                 // per-channel sum / sum of squares of the bf16 values just staged (== what the
                 // next kernel reads back).  Each thread owns one 32-bit word column (2 channels)
@@ -421,18 +465,23 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                         }
                 }
             }
-            if (te == 0) SDN_DBG(2, dbg_tile, 5);
+            if (dbg_lead) SDN_DBG(2, dbg_tile, 5);
             sbuf = (Cfg::DBUF == 2) ? (sbuf ^ 1) : 0;
-            a ^= 1;
-            if (a == 0) aph ^= 1;
+            if (EG == 2) {
+                aph ^= 1;
+            } else {
+                a ^= 1;
+                if (a == 0) aph ^= 1;
+            }
         }
         if (do_stats) {
             // one cross-row-group reduction per kernel: scratch[rg][channel] -> per-CTA partials
-            float* dst = p.stats_partials + size_t(blockIdx.x) * 2 * p.n_total;
+            float* dst = p.stats_partials + size_t(blockIdx.x * EG + eg) * 2 * p.n_total;
+            scratch += eg * (Cfg::SCRATCH_BYTES / 4 / EG);
 #pragma unroll
             for (int nt = 0; nt < Cfg::NT; ++nt) {
                 if (nt * BLOCK_N >= p.n_total) break;
-                ptx::named_bar_sync(2, 128);
+                ptx::named_bar_sync(3 + eg, 128);
 #pragma unroll
                 for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
                     const int chn = cbk * Cfg::DCH + 2 * st_w;
@@ -441,7 +490,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                     scratch[Cfg::RG * BLOCK_N + st_rg * BLOCK_N + chn] = st_acc[nt][cbk][2];
                     scratch[Cfg::RG * BLOCK_N + st_rg * BLOCK_N + chn + 1] = st_acc[nt][cbk][3];
                 }
-                ptx::named_bar_sync(2, 128);
+                ptx::named_bar_sync(3 + eg, 128);
                 for (int c = te; c < BLOCK_N; c += 128) {
                     float sum = 0.f, sq = 0.f;
 #pragma unroll

@@ -50,7 +50,9 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 // row-halo K order (conv_gemm HALO): k = ((dx*blocks + cb)*3 + dy)*KB + c, channel = cb*KB + c, tap = dy*3 + dx
 // mode 5: conv3x3 forward   dst[co][k]                    = W[co][channel][tap]           (Kpad = KB)
 // mode 6: conv3x3 dgrad     dst[ci][k]                    = W[channel][ci][8 - tap]       (Kpad = KB)
-// oscale (modes 0, 2, 5 only): per-output-channel factor folded into the packed weights
+// box9 K order (conv_gemm HALO = 2): k = (cb*9 + tap)*KB + c
+// mode 8: conv3x3 forward   dst[co][k] = W[co][channel][tap];  mode 9: dgrad  dst[ci][k] = W[channel][ci][8 - tap]
+// oscale (modes 0, 2, 5, 8 only): per-output-channel factor folded into the packed weights
 // (eval-mode BatchNorm: w' = w * gamma / sqrt(running_var + eps)); nullptr = 1.
 __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mode, int Co, int Ci, int Kpad,
                                             const float* __restrict__ oscale, int i) {
@@ -79,6 +81,14 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mod
         const int chan = cb * KB + c, tap = dy * 3 + dx;
         v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
         if (mode == 5 && oscale != nullptr) v *= oscale[row];
+    } else if (mode == 8 || mode == 9) {
+        const int KB = Kpad;
+        const int kin = mode == 8 ? Ci : Co;
+        const int row = i / (9 * kin), k = i % (9 * kin);
+        const int c = k % KB, tap = (k / KB) % 9, cb = k / (9 * KB);
+        const int chan = cb * KB + c;
+        v = mode == 8 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
+        if (mode == 8 && oscale != nullptr) v *= oscale[row];
     } else if (mode == 3) {
         const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
         v = w[(ci * Co + co) * 4 + q];
@@ -707,6 +717,18 @@ __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restri
     }
 }
 
+// Zero fills as kernels: cudaMemsetAsync may be served by a copy engine, where it would queue behind a
+// bulk host->device prefetch running on another stream.
+__global__ void zero_u64_kernel(unsigned long long* __restrict__ p, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0ull;
+}
+__global__ void __launch_bounds__(256) zero_u32_kernel(uint32_t* __restrict__ p, size_t n) {
+    const size_t n4 = n / 4;
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x)
+        p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = n4 * 4 + blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = 0u;
+}
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int accumulate) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (accumulate) dst[i] += src[i]; else dst[i] = src[i];

@@ -148,7 +148,7 @@ struct Act {
 struct GemmOp {
     ConvGemmParams p;
     int swa = 128, block_n = 32, grid = 1, smem = 0;
-    bool halo = false;  // row-halo A boxes (3x3 convs); the packed weights use the matching K order
+    int halo = 0;  // 3x3 convs: 1 = row-halo A boxes (one per horizontal tap), 2 = one box for all nine taps; the packed weights use the matching K order
 };
 struct WgradOp {
     WgradParams p;
@@ -201,6 +201,7 @@ struct sdn_ctx {
     unsigned long long* n_local = nullptr;  // device u64
     float* gray_part = nullptr;
     float* blur_tmp = nullptr;
+    float* aug_stage = nullptr;   // device copy of pinned-host augmentation parameters (2*maxB structs)
     size_t blur_tmp_elems = 0;
     const float* params[SDN_NUM_PARAMS] = {};
     float* grads[SDN_NUM_PARAMS] = {};
@@ -257,40 +258,54 @@ static inline int lvl_h(const sdn_ctx* c, int lvl) { return c->H >> (lvl - 1); }
 static inline int lvl_w(const sdn_ctx* c, int lvl) { return c->W >> (lvl - 1); }
 
 // -------------------------------------------------------------- launchers
-template <int SWA, int BN, bool HALO>
+template <int SWA, int BN, int HALO>
 static int launch_cg_t(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
-    conv_gemm_kernel<SWA, BN, HALO><<<op.grid, 192, op.smem, st>>>(op.p);
+    conv_gemm_kernel<SWA, BN, HALO><<<op.grid, CgCfg<SWA, BN>::THREADS, op.smem, st>>>(op.p);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
-    if (op.halo) {
+    if (op.halo == 2) {
         if (op.swa == 128) {
             switch (op.block_n) {
-                case 32: return launch_cg_t<128, 32, true>(c, op, st);
-                case 64: return launch_cg_t<128, 64, true>(c, op, st);
-                case 128: return launch_cg_t<128, 128, true>(c, op, st);
+                case 32: return launch_cg_t<128, 32, 2>(c, op, st);
+                case 64: return launch_cg_t<128, 64, 2>(c, op, st);
             }
         } else if (op.swa == 64) {
             switch (op.block_n) {
-                case 32: return launch_cg_t<64, 32, true>(c, op, st);
-                case 64: return launch_cg_t<64, 64, true>(c, op, st);
+                case 32: return launch_cg_t<64, 32, 2>(c, op, st);
+                case 64: return launch_cg_t<64, 64, 2>(c, op, st);
+            }
+        }
+        return fail("no box9 conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
+    }
+    if (op.halo) {
+        if (op.swa == 128) {
+            switch (op.block_n) {
+                case 32: return launch_cg_t<128, 32, 1>(c, op, st);
+                case 64: return launch_cg_t<128, 64, 1>(c, op, st);
+                case 128: return launch_cg_t<128, 128, 1>(c, op, st);
+            }
+        } else if (op.swa == 64) {
+            switch (op.block_n) {
+                case 32: return launch_cg_t<64, 32, 1>(c, op, st);
+                case 64: return launch_cg_t<64, 64, 1>(c, op, st);
             }
         }
         return fail("no row-halo conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
     }
     if (op.swa == 128) {
         switch (op.block_n) {
-            case 32: return launch_cg_t<128, 32, false>(c, op, st);
-            case 64: return launch_cg_t<128, 64, false>(c, op, st);
-            case 128: return launch_cg_t<128, 128, false>(c, op, st);
-            case 256: return launch_cg_t<128, 256, false>(c, op, st);
+            case 32: return launch_cg_t<128, 32, 0>(c, op, st);
+            case 64: return launch_cg_t<128, 64, 0>(c, op, st);
+            case 128: return launch_cg_t<128, 128, 0>(c, op, st);
+            case 256: return launch_cg_t<128, 256, 0>(c, op, st);
         }
     } else if (op.swa == 64) {
         switch (op.block_n) {
-            case 32: return launch_cg_t<64, 32, false>(c, op, st);
-            case 64: return launch_cg_t<64, 64, false>(c, op, st);
+            case 32: return launch_cg_t<64, 32, 0>(c, op, st);
+            case 64: return launch_cg_t<64, 64, 0>(c, op, st);
         }
     }
     return fail("no conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
@@ -312,10 +327,11 @@ static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
 static int set_smem_attrs() {
     const int big = 227 * 1024;
 #define SDN_SMEM_ATTR(...) CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
-    SDN_SMEM_ATTR(128, 32, false); SDN_SMEM_ATTR(128, 64, false); SDN_SMEM_ATTR(128, 128, false);
-    SDN_SMEM_ATTR(128, 256, false); SDN_SMEM_ATTR(64, 32, false); SDN_SMEM_ATTR(64, 64, false);
-    SDN_SMEM_ATTR(128, 32, true); SDN_SMEM_ATTR(128, 64, true); SDN_SMEM_ATTR(128, 128, true);
-    SDN_SMEM_ATTR(64, 32, true); SDN_SMEM_ATTR(64, 64, true);
+    SDN_SMEM_ATTR(128, 32, 0); SDN_SMEM_ATTR(128, 64, 0); SDN_SMEM_ATTR(128, 128, 0);
+    SDN_SMEM_ATTR(128, 256, 0); SDN_SMEM_ATTR(64, 32, 0); SDN_SMEM_ATTR(64, 64, 0);
+    SDN_SMEM_ATTR(128, 32, 1); SDN_SMEM_ATTR(128, 64, 1); SDN_SMEM_ATTR(128, 128, 1);
+    SDN_SMEM_ATTR(64, 32, 1); SDN_SMEM_ATTR(64, 64, 1);
+    SDN_SMEM_ATTR(128, 32, 2); SDN_SMEM_ATTR(128, 64, 2); SDN_SMEM_ATTR(64, 32, 2); SDN_SMEM_ATTR(64, 64, 2);
 #undef SDN_SMEM_ATTR
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -409,12 +425,29 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     }
     if (n_per_dmap % bn != 0) return fail("build_gemm: N %d not divisible by BLOCK_N %d", n_per_dmap, bn);
     op.block_n = bn;
-    op.halo = conv3x3 && bn <= g_halo_max_n;
+    op.halo = (conv3x3 && bn <= g_halo_max_n) ? 1 : 0;
     Tile t = choose_tile(W, H, B, 128);
-    if (op.halo) {
+    static int box9_on = -1, bres_max = -1;
+    if (box9_on < 0) { const char* e = getenv("SDN_BOX9"); box9_on = e ? atoi(e) : 1; }
+    if (bres_max < 0) { const char* e = getenv("SDN_BRES_MAXKB"); bres_max = (e ? atoi(e) : 80) * 1024; }
+    {
+        // box9: one (TH+2)x(TW+2) box per (source, channel block) feeds all nine taps; needs the whole
+        // packed weight matrix resident in shared memory and 8-pixel-wide tiles
+        int cin_tot = 0;
+        for (const SrcView& v : aviews) cin_tot += v.C;
+        if (op.halo && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max) op.halo = 2;
+    }
+    if (op.halo == 2) {
+        t = Tile{8, 16, 1};
+        segs.clear();
+        for (int sv = 0; sv < (int)aviews.size(); ++sv) segs.push_back({sv, 0, 0});
+    } else if (op.halo) {
         // one image per box and TW % 8 == 0 so the vertical-tap row shifts are whole swizzle groups
         double best = 1e300;
+        static int force_tw = -1;
+        if (force_tw < 0) { const char* e = getenv("SDN_HALO_TW"); force_tw = e ? atoi(e) : 0; }
         for (int TW = 8; TW <= 32; TW *= 2) {
+            if (force_tw && TW != force_tw) continue;
             const int TH = 128 / TW;
             const double padded = double((W + TW - 1) / TW * TW) * double((H + TH - 1) / TH * TH);
             const double cost = padded * double(TH + 2) / double(TH);
@@ -433,10 +466,10 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
-        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, t.TW, op.halo ? t.TH + 2 : t.TH,
-                       t.TN, op.swa));
+        SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, KB, op.halo == 2 ? t.TW + 2 : t.TW,
+                       op.halo ? t.TH + 2 : t.TH, t.TN, op.swa));
     }
-    p.a_stage_bytes = (t.TW * (t.TH + 2) * op.swa + 1023) & ~1023;
+    p.a_stage_bytes = ((op.halo == 2 ? t.TW + 2 : t.TW) * (t.TH + 2) * op.swa + 1023) & ~1023;
     for (size_t i = aviews.size(); i < 4; ++i) p.a_maps[i] = p.a_maps[0];
     int kblocks = 0;
     p.nsegs = (int)segs.size();
@@ -450,7 +483,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         kblocks += g.cblocks;
     }
     p.kblocks_total = kblocks;
-    if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * 3, bn, op.swa));
+    if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * (op.halo == 2 ? 9 : 3), bn, op.swa));
     else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
     const int swd = bn >= 64 ? 128 : 64;
     const int dch = swd / 2;
@@ -467,12 +500,22 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.stats_partials = stats_partials;
     if ((flags & CG_STATS) && n_total > 512) return fail("build_gemm: stats need n_total <= 512");
     int stages = 8;
-    if (op.halo) {
+    if (op.halo == 2) {
+        const int b_total = kblocks * 9 * bn * op.swa;
+        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);
+        p.flags |= CG_BRES;
+        p.b_res_bytes = b_total;
+        const int budget = 220 * 1024 - fixed - b_total;
+        // every unit of a tile in one stage when at least three such stages fit
+        p.ups = (kblocks <= 3 && budget / (kblocks * p.a_stage_bytes) >= 3) ? kblocks : 1;
+        stages = std::max(2, std::min(8, budget / (p.ups * p.a_stage_bytes)));
+        op.smem = fixed + b_total + stages * p.ups * p.a_stage_bytes;
+        if (op.smem > 227 * 1024) return fail("build_gemm: box9 shared memory %d", op.smem);
+    } else if (op.halo) {
         // weights resident in shared memory when the whole packed matrix of this N tile fits;
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
         const int b_total = kblocks * 3 * bn * op.swa;
-        static int bres_max = -1, ups_on = -1;
-        if (bres_max < 0) { const char* e = getenv("SDN_BRES_MAXKB"); bres_max = (e ? atoi(e) : 80) * 1024; }
+        static int ups_on = -1;
         if (ups_on < 0) { const char* e = getenv("SDN_UPS"); ups_on = e ? atoi(e) : 3; }
         const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
@@ -676,6 +719,7 @@ static int plan_and_alloc(sdn_ctx* c) {
         carve(cur, (size_t)2 * B * parts * sizeof(float), (void**)&c->gray_part);
         c->blur_tmp_elems = (size_t)2 * B * 3 * c->H * c->W;
         carve(cur, c->blur_tmp_elems * sizeof(float), (void**)&c->blur_tmp);
+        carve(cur, (size_t)2 * B * sizeof(AugParams), (void**)&c->aug_stage);
         if (pass == 0) {
             c->ws_bytes = (size_t)(cur - (uint8_t*)nullptr) + 4096;
             CUDA_OK(cudaMalloc((void**)&c->ws, c->ws_bytes));
@@ -769,6 +813,16 @@ static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
     return (int)std::max(1LL, std::min(need, cap));
 }
 
+static int zero_fill(sdn_ctx* c, void* p, size_t bytes, cudaStream_t st) {
+    if (bytes % 4 != 0) return fail("zero_fill: %zu bytes not a multiple of 4", bytes);
+    const size_t words = bytes / 4;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((words / 4 + 255) / 256, (size_t)c->num_sms * 8));
+    zero_u32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<uint32_t*>(p), words);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // bf16 operand cache <- fp32 parameters: one launch for every layer
 static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
     ProfScope ps(c, st, "pack_weights", 0, 0.0, 7763938.0 * (4 + 2) * (training ? 2 : 1));
@@ -789,8 +843,9 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
             add(w, L.wf, fold ? L.scale : nullptr, 2, L.cout, L.cin, 64, L.cout * 64);
         } else {
             const int n = 9 * L.cin * L.cout;
-            add(w, L.wf, fold ? L.scale : nullptr, L.fprop.halo ? 5 : 0, L.cout, L.cin, L.fprop.swa / 2, n);
-            if (training) add(w, L.wd, nullptr, L.dgrad.halo ? 6 : 1, L.cout, L.cin, L.dgrad.swa / 2, n);
+            static const int fmode[3] = {0, 5, 8}, dmode[3] = {1, 6, 9};
+            add(w, L.wf, fold ? L.scale : nullptr, fmode[(fold ? L.fprop_eval : L.fprop).halo], L.cout, L.cin, L.fprop.swa / 2, n);
+            if (training) add(w, L.wd, nullptr, dmode[L.dgrad.halo], L.cout, L.cin, L.dgrad.swa / 2, n);
         }
     }
     for (int k = 0; k < 4; ++k) {
@@ -891,7 +946,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
         if (training) {
             const double count = (double)B * L.y.H * L.y.W;
             bn_finalize_train_kernel<<<(L.cout * 32 + 255) / 256, 256, 0, st>>>(
-                c->stats_partials, op.grid, L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
+                c->stats_partials, op.grid * (op.block_n <= 64 ? 2 : 1), L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
                 c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd);
             ++c->launches;
         }
@@ -1010,8 +1065,8 @@ static int head_grads_out(sdn_ctx* c, cudaStream_t st) {
 static int backward_prologue(sdn_ctx* c, int accumulate, cudaStream_t st) {
     if (!c->have_forward_train) return fail("backward without a training-mode forward");
     c->accumulate = accumulate;
-    CUDA_OK(cudaMemsetAsync(c->wg_all, 0, c->wg_all_bytes, st));
-    CUDA_OK(cudaMemsetAsync(c->head_grads, 0, 128 * sizeof(float), st));
+    SDN_OK(zero_fill(c, c->wg_all, c->wg_all_bytes, st));
+    SDN_OK(zero_fill(c, c->head_grads, 128 * sizeof(float), st));
     return 0;
 }
 
@@ -1161,7 +1216,7 @@ int sdn_count_valid(sdn_ctx* c, const float* target, const uint8_t* mask, int B,
         return fail("sdn_count_valid: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaSetDevice(c->device));
-    CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(unsigned long long), st));
+    SDN_OK(zero_fill(c, count_out, sizeof(unsigned long long), st));
     const long long npix = (long long)B * c->H * c->W;
     mask_count_kernel<<<ew_grid(c, npix, 256), 256, 0, st>>>(target, mask, npix, count_out);
     ++c->launches;
@@ -1185,8 +1240,8 @@ int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* 
             n_norm_dev = c->n_local;
         }
     } else {
-        CUDA_OK(cudaMemsetAsync(c->head_grads, 0, 128 * sizeof(float), st));
-        CUDA_OK(cudaMemsetAsync(c->n_local, 0, sizeof(unsigned long long), st));
+        SDN_OK(zero_fill(c, c->head_grads, 128 * sizeof(float), st));
+        SDN_OK(zero_fill(c, c->n_local, sizeof(unsigned long long), st));
         n_norm_dev = c->n_local;  // zero -> gradients are zero and unused
     }
     // the gradient buffer of dec1's output doubles as scratch on the metrics-only path
@@ -1248,8 +1303,14 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     if (Hs < 1 || Ws < 1) return fail("sdn_preprocess: bad source size %dx%d", Hs, Ws);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaSetDevice(c->device));
-    if (valid_count != nullptr) CUDA_OK(cudaMemsetAsync(valid_count, 0, sizeof(unsigned long long), st));
+    if (valid_count != nullptr) SDN_OK(zero_fill(c, valid_count, sizeof(unsigned long long), st));
     const AugParams* aug_all = reinterpret_cast<const AugParams*>(aug_dev);
+    if (aug_all != nullptr && (flags & SDN_PREPROCESS_AUG_HOST)) {
+        const int words = 2 * B * (int)(sizeof(AugParams) / 4);
+        copy_f32_kernel<<<(words + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(aug_dev), c->aug_stage, words, 0);
+        ++c->launches;
+        aug_all = reinterpret_cast<const AugParams*>(c->aug_stage);
+    }
     // With augmentation on, samples go through in chunks whose fp32 views stay L2-resident between the
     // decode/resize pass and the in-place augmentation pass, so DRAM sees each byte about once.
     static int chunk_cfg = -1;

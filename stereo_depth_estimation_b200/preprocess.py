@@ -85,7 +85,7 @@ class AugmentSampler:
 
     def sample_packed(self, batch: int) -> torch.Tensor:
         """The same distributions drawn for a whole batch at once (numpy, vectorised) and
-        returned as the packed sdn_aug_params array (host uint8 tensor, pinned if possible)."""
+        returned as the packed sdn_aug_params array (host uint8 tensor)."""
         n = 2 * batch
         rec = np.zeros(n, dtype=AUG_DTYPE)
 
@@ -106,15 +106,7 @@ class AugmentSampler:
         if self.noise_std_max > 0:
             rec["noise_std"] = self.rng.uniform(0.0, self.noise_std_max, n)
         rec["noise_seed"] = self.rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32)
-        raw = torch.from_numpy(rec.view(np.uint8))
-        if not torch.cuda.is_available():
-            return raw.clone()
-        # a small ring of pinned staging buffers (cudaHostAlloc per call is slow; the H2D copy is async)
-        ring = self.__dict__.setdefault("_pinned_ring", {})
-        bufs = ring.setdefault(raw.numel(), [torch.empty(raw.numel(), dtype=torch.uint8).pin_memory() for _ in range(4)])
-        slot = self.__dict__["_ring_pos"] = (self.__dict__.get("_ring_pos", -1) + 1) % 4
-        bufs[slot].copy_(raw)
-        return bufs[slot]
+        return torch.from_numpy(rec.view(np.uint8).copy())
 
 
 AUG_DTYPE = np.dtype([("brightness", "<f4"), ("contrast", "<f4"), ("saturation", "<f4"), ("hue", "<f4"),
@@ -122,14 +114,14 @@ AUG_DTYPE = np.dtype([("brightness", "<f4"), ("contrast", "<f4"), ("saturation",
 
 
 def pack_aug(views: Sequence[ViewAug]) -> torch.Tensor:
-    """Host (pinned when CUDA is present) uint8 tensor holding the sdn_aug_params array."""
+    """Host uint8 tensor holding the sdn_aug_params array (DevicePreprocessor stages it in pinned memory)."""
     arr = (_lib.AugParams * len(views))()
     for i, v in enumerate(views):
         arr[i] = _lib.AugParams(v.brightness, v.contrast, v.saturation, v.hue, v.gamma, v.blur_sigma, v.noise_std,
                                 v.noise_seed & 0xFFFFFFFF)
     raw = np.frombuffer(arr, dtype=np.uint8).copy()
     t = torch.from_numpy(raw)
-    return t.pin_memory() if torch.cuda.is_available() else t
+    return t
 
 
 class DevicePreprocessor:
@@ -146,6 +138,10 @@ class DevicePreprocessor:
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(lib.sdn_create(ctypes.byref(self.ctx), index, self.max_batch, self.image_size[0],
                                   self.image_size[1], _lib.CTX_PREPROCESS_ONLY))
+        depth = 4   # augmentation-parameter ring: the host may run this many steps ahead of the device
+        self._ring = [torch.empty(2 * self.max_batch * 32, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self._ring_ev = [torch.cuda.Event() for _ in range(depth)]
+        self._ring_pos = -1
 
     def close(self) -> None:
         if getattr(self, "ctx", None) is not None and self.ctx:
@@ -192,7 +188,18 @@ class DevicePreprocessor:
             packed = aug if torch.is_tensor(aug) else pack_aug(aug)   # list of ViewAug or sample_packed() output
             if packed.numel() != 2 * b * 32:
                 raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {packed.numel() // 32}")
-            aug_dev = packed.to(self.device, non_blocking=True)
+            flags_aug = 0
+            if packed.is_cuda:
+                aug_dev = packed
+            else:
+                # event-guarded ring of pinned buffers that the device reads in place (a staging KERNEL,
+                # not a copy-engine transfer: it cannot queue behind a bulk prefetch of the next batch)
+                slot = self._ring_pos = (self._ring_pos + 1) % len(self._ring_ev)
+                self._ring_ev[slot].synchronize()
+                buf = self._ring[slot][: packed.numel()]
+                buf.copy_(packed)
+                aug_dev = buf
+                flags_aug = _lib.PREPROCESS_AUG_HOST
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(
             _lib.load().sdn_preprocess(
@@ -200,9 +207,9 @@ class DevicePreprocessor:
                 aug_dev.data_ptr() if aug_dev is not None else None,
                 out["input"].data_ptr(), out["target"].data_ptr(), out["valid_mask"].data_ptr(),
                 count_out.data_ptr() if count_out is not None else None,
-                _lib.RESIZE_FOURTERM if fourterm else 0, stream,
+                (_lib.RESIZE_FOURTERM if fourterm else 0) | (flags_aug if aug_dev is not None else 0), stream,
             )
         )
-        if aug_dev is not None:
-            aug_dev.record_stream(torch.cuda.current_stream(self.device))
+        if aug_dev is not None and not aug_dev.is_cuda:
+            self._ring_ev[self._ring_pos].record(torch.cuda.current_stream(self.device))
         return out

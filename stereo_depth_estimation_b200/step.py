@@ -123,7 +123,7 @@ class FusedStep:
             _lib.check(lib.sdn_count_valid(eng.ctx, target.data_ptr(), mask.data_ptr(), x.shape[0],
                                            self.n_norm.data_ptr(), stream))
         else:
-            self.n_norm.copy_(valid_count.view(1), non_blocking=True)
+            torch.add(valid_count.view(1), 0, out=self.n_norm)   # a kernel, not a copy-engine transfer
         if self.world > 1:
             dist.all_reduce(self.n_norm, group=self.group)
 
