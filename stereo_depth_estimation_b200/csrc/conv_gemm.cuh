@@ -50,7 +50,7 @@ struct alignas(64) ConvGemmParams {
     int TW, TH, TN;                 // pixel box, TW*TH*TN == 128
     int img_w, img_h, img_n;        // output extent (rows of a ragged box outside it are zeroed)
     int n_tiles;                    // N tiling
-    int n_tiles_per_dmap;           // N tiles that land in one D map
+    int n_per_dmap;                 // output channels per destination map (a tile may span several maps)
     int n_total;                    // n_tiles * BLOCK_N
     int flags;
     int stages;
@@ -81,7 +81,9 @@ struct CgCfg {
     static constexpr int A_BYTES = 128 * SWA;
     static constexpr int B_BYTES = BLOCK_N * SWA;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SWD = BLOCK_N >= 64 ? 128 : 64;  // staging / store swizzle
+    // staging / store swizzle: 64-channel blocks, except 32-channel blocks for N = 32 and for 32-channel
+    // sources (so that a 64-wide tile can be split over two 32-channel destinations: dec1 dgrad)
+    static constexpr int SWD = (BLOCK_N >= 64 && SWA == 128) ? 128 : 64;
     static constexpr int DCH = SWD / 2;                   // channels per D block
     static constexpr int D_BLOCKS = BLOCK_N / DCH;
     static constexpr int D_BLOCK_BYTES = 128 * SWD;
@@ -274,35 +276,39 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                     const bool leader = ptx::elect_one();   // one election per stage
                     if (SDN_ABLATE(CG_DBG_NOMMA)) {
                     } else if (HALO == 2) {
-                        const uint32_t row_pitch = uint32_t(p.TW + 2) * SWA;   // box row = TW+2 pixels
+                        constexpr uint32_t ROW_PITCH = 10 * SWA;   // box row = TW + 2 = 10 pixels
+                        const uint32_t lead = leader ? 1u : 0u;
                         for (int j = 0; j < ups; ++j) {
-                            const uint32_t a_addr = st_addr + j * unit_bytes;
-                            const uint32_t b_addr = b_res_addr + (kb + j) * 9 * Cfg::B_BYTES;
+                            // one descriptor pair per unit; every tap / k-step is a compile-time offset of the
+                            // 14-bit (address >> 4) field, and the issue is predicated, not branched
+                            const uint64_t a0 = ptx::make_smem_desc(st_addr + j * unit_bytes, 16, ROW_PITCH, LAYOUT_A);
+                            const uint64_t b0 =
+                                ptx::make_smem_desc(b_res_addr + (kb + j) * 9 * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                             for (int tap = 0; tap < 9; ++tap) {
-                                const uint64_t adesc = ptx::make_smem_desc(
-                                    a_addr + (tap / 3) * row_pitch + (tap % 3) * SWA, 16, row_pitch, LAYOUT_A);
-                                const uint64_t bdesc = ptx::make_smem_desc(b_addr + tap * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    if (leader)
-                                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                         (kb | j | tap | k) != 0 ? 1u : 0u);
+                                    ptx::tc_mma_bf16_pred(
+                                        tmem_d, a0 + uint64_t(((tap / 3) * ROW_PITCH + (tap % 3) * SWA) / 16 + 2 * k),
+                                        b0 + uint64_t(tap * Cfg::B_BYTES / 16 + 2 * k), IDESC,
+                                        (tap | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);
                             }
                         }
                     } else if (HALO == 1) {
+                        const uint32_t lead = leader ? 1u : 0u;
+                        const uint64_t dy_step = uint64_t(uint32_t(p.TW * SWA) >> 4);
                         for (int j = 0; j < ups; ++j) {
                             const uint32_t a_addr = st_addr + j * unit_bytes;
                             const uint32_t b_addr = bres ? b_res_addr + (kb + j) * 3 * Cfg::B_BYTES : a_addr + a_bytes;
+                            const uint64_t a0 = ptx::make_smem_desc(a_addr, 16, SBO_A, LAYOUT_A);
+                            const uint64_t b0 = ptx::make_smem_desc(b_addr, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy) {
-                                const uint64_t adesc = ptx::make_smem_desc(a_addr + dy * p.TW * SWA, 16, SBO_A, LAYOUT_A);
-                                const uint64_t bdesc = ptx::make_smem_desc(b_addr + dy * Cfg::B_BYTES, 16, SBO_A, LAYOUT_A);
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    if (leader)
-                                        ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                         (kb | j | dy | k) != 0 ? 1u : 0u);
+                                    ptx::tc_mma_bf16_pred(tmem_d, a0 + dy * dy_step + uint64_t(2 * k),
+                                                          b0 + uint64_t(dy * Cfg::B_BYTES / 16 + 2 * k), IDESC,
+                                                          (dy | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);
                             }
                         }
                     } else {
@@ -313,9 +319,8 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k) {
                             // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-                            if (leader)
-                                ptx::tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                 (kb | k) != 0 ? 1u : 0u);
+                            ptx::tc_mma_bf16_pred(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                                  k != 0 ? 1u : (kb != 0 ? 1u : 0u), leader ? 1u : 0u);
                         }
                     }
                     if (leader) ptx::tc_commit(&empty_bar[s]);
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                 for (int k = 0; k < 4; ++k) st_acc[i][j][k] = 0.f;
         int sbuf = 0;
         int dbg_it = 0;
-        const int dmap_div = p.n_tiles_per_dmap;
+        const int dmap_div = p.n_per_dmap;   // channels per destination map
         ptx::TileWalker tw;
         for (tw.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid();
              tw.next()) {
@@ -426,13 +431,15 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
             if (dbg_lead) SDN_DBG(2, dbg_tile, 4);
 
             if (te == 0 && !SDN_ABLATE(CG_DBG_NOSTORE)) {
-                int dmap = 0, nrem = n_tile;   // n_tile / n_tiles_per_dmap without a division (<= 4 maps)
-                while (nrem >= dmap_div) { nrem -= dmap_div; ++dmap; }
-                const int cbase = nrem * BLOCK_N;
+                // channel block -> (destination map, channel inside it) without a division (<= 4 maps)
+                int dmap = 0, cbase = n_tile * BLOCK_N;
+                while (cbase >= dmap_div) { cbase -= dmap_div; ++dmap; }
 #pragma unroll
-                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk)
-                    ptx::tma_store_4d(&p.d_maps[dmap], stg + cbk * Cfg::D_BLOCK_BYTES, cbase + cbk * Cfg::DCH, x0, y0,
-                                      n0);
+                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
+                    ptx::tma_store_4d(&p.d_maps[dmap], stg + cbk * Cfg::D_BLOCK_BYTES, cbase, x0, y0, n0);
+                    cbase += Cfg::DCH;
+                    if (cbase >= dmap_div) { cbase -= dmap_div; ++dmap; }
+                }
                 ptx::tma_store_commit();
             }
             if (dbg_lead) SDN_DBG(2, dbg_tile, 6);

@@ -416,6 +416,12 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     op.swa = all64 ? 128 : 64;
     const int KB = op.swa / 2;
     int bn = std::min(n_per_dmap, 256);
+    // narrow destinations (dgrad of a concat input): one tile spans both, so the A operand is fetched once
+    if (n_per_dmap < 128 && n_total > n_per_dmap) {
+        int wide = std::min(n_total, op.swa == 64 ? 64 : 128);
+        const int wide_dch = (wide >= 64 && op.swa == 128) ? 64 : 32;   // store block of that tile width
+        if (wide % n_per_dmap == 0 && n_per_dmap % wide_dch == 0) bn = wide;
+    }
     if (op.swa == 64 && bn > 64) bn = 64;
     const int W = dviews[0].W, H = dviews[0].H;
     if (!(flags & CG_STATS)) {
@@ -423,7 +429,8 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         const long long m_est = ((long long)W * H * B + 127) / 128;
         while (bn > 32 && m_est * (n_total / bn) < c->num_sms / 2) bn /= 2;
     }
-    if (n_per_dmap % bn != 0) return fail("build_gemm: N %d not divisible by BLOCK_N %d", n_per_dmap, bn);
+    if (n_per_dmap % bn != 0 && bn % n_per_dmap != 0)
+        return fail("build_gemm: N %d and BLOCK_N %d do not nest", n_per_dmap, bn);
     op.block_n = bn;
     op.halo = (conv3x3 && bn <= g_halo_max_n) ? 1 : 0;
     Tile t = choose_tile(W, H, B, 128);
@@ -485,15 +492,16 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.kblocks_total = kblocks;
     if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * (op.halo == 2 ? 9 : 3), bn, op.swa));
     else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
-    const int swd = bn >= 64 ? 128 : 64;
+    const int swd = (bn >= 64 && op.swa == 128) ? 128 : 64;
     const int dch = swd / 2;
+    if (n_per_dmap % dch != 0) return fail("build_gemm: destination width %d not a multiple of the %d-channel store block", n_per_dmap, dch);
     for (size_t i = 0; i < dviews.size(); ++i) {
         const SrcView& v = dviews[i];
         SDN_OK(encode4(&p.d_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, dch, t.TW, t.TH, t.TN, swd));
     }
     for (size_t i = dviews.size(); i < 4; ++i) p.d_maps[i] = p.d_maps[0];
     p.n_tiles = n_total / bn;
-    p.n_tiles_per_dmap = n_per_dmap / bn;
+    p.n_per_dmap = n_per_dmap;
     p.n_total = n_total;
     p.flags = flags;
     p.bias = bias;
