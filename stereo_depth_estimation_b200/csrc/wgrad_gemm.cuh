@@ -179,8 +179,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 ptx::tc_fence_after();
                 const uint64_t sa = adesc0 + uint64_t(s * stage16);
                 const uint64_t sb = bdesc0 + uint64_t(s * stage16);
-                if (TR) {
-                    if (ptx::elect_one()) {
+                // one election per stage.  Where it measured faster (32-channel swapped-role units, the deep
+                // row-halo layers) the MMAs are PREDICATED on it and the warp stays converged; elsewhere the
+                // elected lane branches around the whole sequence.
+                constexpr bool PRED = TR ? (CA == 32) : HALO;
+                const bool leader = ptx::elect_one();
+                const uint32_t lead = leader ? 1u : 0u;
+                if (PRED || leader) {
+                    if (TR) {
                         // stage-0 descriptors + (stage, k-step, unit) offsets in the 14-bit address field
                         const uint64_t ys = tr_ydesc0 + uint64_t(s * stage16);
                         const uint64_t xs = tr_xdesc0 + uint64_t(s * stage16);
@@ -194,31 +200,31 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                                 if (g < nunits) {
                                     const uint64_t xdesc = xk + uint64_t(g * b_unit16);
                                     if (CA == 32) {
-                                        ptx::tc_mma_bf16(tmem_base + g * tr_cout, xdesc, ydesc, tr_idesc128, acc);
+                                        ptx::tc_mma_bf16_pred(tmem_base + g * tr_cout, xdesc, ydesc, tr_idesc128, acc, lead);
                                     } else {
                                         ptx::tc_mma_bf16(tmem_base + g * 2 * tr_cout, xdesc, ydesc, tr_idesc128, acc);
-                                        ptx::tc_mma_bf16(tmem_base + g * 2 * tr_cout + tr_cout, xdesc + uint64_t(tr_dy2_16), ydesc,
-                                                         tr_idesc64, acc);
+                                        ptx::tc_mma_bf16(tmem_base + g * 2 * tr_cout + tr_cout, xdesc + uint64_t(tr_dy2_16),
+                                                         ydesc, tr_idesc64, acc);
                                     }
                                 }
                             }
                         }
-                        ptx::tc_commit(&empty_bar[s]);
-                    }
-                } else
-                if (ptx::elect_one()) {   // one election per stage; the elected lane issues the stage's MMAs
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
-                        const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
-                        const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
-                        const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                        for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
+                            const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
+                            const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
+                            const uint32_t acc = (it | k) != 0 ? 1u : 0u;
 #pragma unroll
-                        for (int g = 0; g < (HALO ? 5 : 8); ++g)
-                            if (g < nmma)
-                                ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
+                            for (int g = 0; g < (HALO ? 5 : 8); ++g)
+                                if (g < nmma) {
+                                    if (PRED) ptx::tc_mma_bf16_pred(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc, lead);
+                                    else ptx::tc_mma_bf16(tmem_base + g * ncol, adesc, bk + uint64_t(g * b_unit16), idesc, acc);
+                                }
+                        }
                     }
-                    ptx::tc_commit(&empty_bar[s]);
                 }
+                if (leader) ptx::tc_commit(&empty_bar[s]);
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
