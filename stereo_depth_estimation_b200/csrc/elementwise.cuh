@@ -249,7 +249,7 @@ __global__ void bn_prepare_eval_kernel(int C, const float* __restrict__ gamma, c
 template <bool POOL>
 __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                                     const float* __restrict__ shift, bf16* __restrict__ a, bf16* __restrict__ pooled,
-                                    int B, int H, int W, int C) {
+                                    unsigned short* __restrict__ amax, int B, int H, int W, int C) {
     const int CG = C >> 3;
     if (POOL) {
         const int H2 = H >> 1, W2 = W >> 1;
@@ -265,6 +265,7 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
 #pragma unroll
             for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cg * 8 + j); sh[j] = __ldg(shift + cg * 8 + j); }
             float mx[8];
+            unsigned am = 0;   // 2 bits per channel: quad position of the FIRST maximum (nn.MaxPool2d routing)
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx[j] = 0.f;  // relu output >= 0
 #pragma unroll
@@ -281,9 +282,12 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
                 float g[8];
                 unpack8(o, g);  // pool the bf16-rounded values (what the consumers will see)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], g[j]);
+                for (int j = 0; j < 8; ++j)
+                    if (d > 0 && g[j] > mx[j]) { mx[j] = g[j]; am = (am & ~(3u << (2 * j))) | (unsigned(d) << (2 * j)); }
+                    else if (d == 0) mx[j] = g[j];
             }
             *reinterpret_cast<uint4*>(pooled + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8) = pack8(mx);
+            if (amax != nullptr) amax[i] = (unsigned short)am;   // the backward pass routes by it instead of recomputing
         }
     } else {
         const long long total = (long long)B * H * W * CG;
@@ -338,7 +342,8 @@ __global__ void maxpool2x2_kernel(const bf16* __restrict__ a, bf16* __restrict__
 // the raw bf16 y vectors and the running arg-max in registers (two passes over the quad).
 template <bool POOL, bool APPLY>
 __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf16* __restrict__ g,
-                                            const bf16* __restrict__ gp, const float (&sc)[8], const float (&sh)[8],
+                                            const bf16* __restrict__ gp, const unsigned short* __restrict__ amax,
+                                            const float (&sc)[8], const float (&sh)[8],
                                             const float (&mu)[8], const float (&rs)[8], const float (&k1)[8],
                                             const float (&k2)[8], long long i, int H, int W, int C, float (&s1)[8],
                                             float (&s2)[8], bf16* __restrict__ dy) {
@@ -352,20 +357,13 @@ __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf
         const int n = int(qd / ((long long)W2 * H2));
         const long long p00 = ((long long)n * H + 2 * y2) * W + 2 * x2;
         const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
-        uint4 yr[4];
-        float best[8];
-        int am[8];
+        // the forward stored which quad position won each channel's max (first maximum, bf16 values)
+        const unsigned am = __ldg(amax + i);
+        uint4 yr[4], gr[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             yr[d] = ldg16(y + pix[d] * C + cg * 8);
-            float yf[8];
-            unpack8(yr[d], yf);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                // the forward pooled the bf16-rounded activation: reproduce it for the arg-max
-                const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yf[j], sc[j], sh[j]), 0.f)));
-                if (d == 0 || a > best[j]) { best[j] = a; am[j] = d; }   // first maximum wins ties
-            }
+            gr[d] = ldg16(g + pix[d] * C + cg * 8);
         }
         float gpf[8];
         unpack8(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gpf);
@@ -373,11 +371,11 @@ __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf
         for (int d = 0; d < 4; ++d) {
             float yf[8], gf[8], o[8];
             unpack8(yr[d], yf);
-            unpack8(ldg16(g + pix[d] * C + cg * 8), gf);
+            unpack8(gr[d], gf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float z = fmaf(yf[j], sc[j], sh[j]);
-                const float da = gf[j] + (am[j] == d ? gpf[j] : 0.f);
+                const float da = gf[j] + (((am >> (2 * j)) & 3u) == unsigned(d) ? gpf[j] : 0.f);
                 const float dz = z > 0.f ? da : 0.f;
                 const float xh = (yf[j] - mu[j]) * rs[j];
                 if (APPLY) o[j] = sc[j] * (dz - k1[j] - xh * k2[j]);
@@ -404,6 +402,7 @@ __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf
 template <bool POOL>
 __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
                                                             const bf16* __restrict__ gp,
+                                                            const unsigned short* __restrict__ amax,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             const float* __restrict__ mean,
@@ -420,7 +419,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
         s1[j] = 0.f; s2[j] = 0.f;
     }
     for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
-        bn_bwd_item<POOL, false>(y, g, gp, sc, sh, mu, rs, sc, sc, i, H, W, C, s1, s2, nullptr);
+        bn_bwd_item<POOL, false>(y, g, gp, amax, sc, sh, mu, rs, sc, sc, i, H, W, C, s1, s2, nullptr);
     __shared__ float red[256][17];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
@@ -462,6 +461,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
 template <bool POOL>
 __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ g,
                                                            const bf16* __restrict__ gp,
+                                                           const unsigned short* __restrict__ amax,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            const float* __restrict__ mean,
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const b
         k1[j] = c1[cg * 8 + j]; k2[j] = c2[cg * 8 + j];
     }
     for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
-        bn_bwd_item<POOL, true>(y, g, gp, sc, sh, mu, rs, k1, k2, i, H, W, C, s1, s2, dy);
+        bn_bwd_item<POOL, true>(y, g, gp, amax, sc, sh, mu, rs, k1, k2, i, H, W, C, s1, s2, dy);
 }
 
 // Per-channel column sum of an NHWC bf16 tensor (ConvTranspose2d bias gradient).

@@ -167,6 +167,7 @@ struct ConvL {  // conv3x3 + BatchNorm + ReLU
     bf16 *wf = nullptr, *wd = nullptr;
     float *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr, *c1 = nullptr, *c2 = nullptr;
     float* wg = nullptr;  // fp32 weight-gradient workspace [9*cin][cout]
+    unsigned short* amax = nullptr;  // pooled layers: 2-bit arg-max per (quad, channel), 8 channels per entry
     GemmOp fprop, fprop_eval, dgrad;   // fprop_eval: BN folded, epilogue = +shift, ReLU, writes `a` directly
     WgradOp wgrad;
     bool has_dgrad = true;
@@ -676,7 +677,10 @@ static int plan_and_alloc(sdn_ctx* c) {
                 act(L.a, L.cout, L.lvl);
                 act(L.dy, L.cout, L.lvl);
                 act(L.ga, L.cout, L.lvl);
-                if (L.pooled_out) { act(L.pool, L.cout, L.lvl + 1); act(L.gp, L.cout, L.lvl + 1); }
+                if (L.pooled_out) {
+                    act(L.pool, L.cout, L.lvl + 1); act(L.gp, L.cout, L.lvl + 1);
+                    carve(cur, L.pool.elems(B) / 8 * sizeof(unsigned short), (void**)&L.amax);
+                }
                 const int kdim = L.first ? 64 : 9 * L.cin;
                 carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wf);
                 carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wd);
@@ -873,12 +877,12 @@ static int run_bn_relu(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     const int H = L.y.H, W = L.y.W, C = L.cout;
     if (L.pooled_out) {
         const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
-        bn_relu_pool_kernel<true><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, L.pool.p, B,
-                                                                         H, W, C);
+        bn_relu_pool_kernel<true><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, L.pool.p,
+                                                                         L.amax, B, H, W, C);
     } else {
         const long long items = (long long)B * H * W * (C / 8);
-        bn_relu_pool_kernel<false><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, nullptr, B,
-                                                                          H, W, C);
+        bn_relu_pool_kernel<false><<<ew_grid(c, items, 256), 256, 0, st>>>(L.y.p, L.scale, L.shift, L.a.p, nullptr,
+                                                                          nullptr, B, H, W, C);
     }
     ++c->launches;
     CUDA_OK(cudaGetLastError());
@@ -982,10 +986,10 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     const long long items = pool ? (long long)B * (H / 2) * (W / 2) * (C / 8) : (long long)B * H * W * (C / 8);
     int grid = (int)std::max(1LL, std::min((items + 255) / 256, (long long)BWD_BLOCKS));
     if (pool)
-        bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.scale, L.shift, L.mean, L.rstd,
+        bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd,
                                                          c->bwd_partials, B, H, W, C);
     else
-        bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, L.scale, L.shift, L.mean, L.rstd,
+        bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
                                                           c->bwd_partials, B, H, W, C);
     ++c->launches;
     bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(c->bwd_partials, grid, C, count, L.c1, L.c2,
@@ -993,10 +997,10 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     ++c->launches;
     const int agrid = ew_grid(c, items, 256);
     if (pool)
-        bn_bwd_apply_kernel<true><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.scale, L.shift, L.mean, L.rstd, L.c1,
+        bn_bwd_apply_kernel<true><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd, L.c1,
                                                          L.c2, L.dy.p, B, H, W, C);
     else
-        bn_bwd_apply_kernel<false><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, L.scale, L.shift, L.mean, L.rstd,
+        bn_bwd_apply_kernel<false><<<agrid, 256, 0, st>>>(L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
                                                           L.c1, L.c2, L.dy.p, B, H, W, C);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
