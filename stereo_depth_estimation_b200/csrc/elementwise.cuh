@@ -150,43 +150,56 @@ constexpr int IM2COL_MAXC = 8;
 template <int Cin>
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
                                                            int H, int W) {
-    __shared__ float tile[Cin * (IM2COL_ROWS + 2)][IM2COL_PX + 2];
+    // +1: one always-zero cell that the k >= 9*Cin padding lanes read (branch-free gather)
+    __shared__ float tile[Cin * (IM2COL_ROWS + 2) * (IM2COL_PX + 2) + 1];
     static_assert(Cin <= IM2COL_MAXC, "first-layer channel count");
     constexpr int K = 9 * Cin;
     constexpr int TR = IM2COL_ROWS + 2;
+    constexpr int PITCH = IM2COL_PX + 2;
+    constexpr int ZERO = Cin * TR * PITCH;
     const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
     const int yblocks = (H + IM2COL_ROWS - 1) / IM2COL_ROWS;
     const int xb = blockIdx.x % xblocks;
     const int yb = (blockIdx.x / xblocks) % yblocks;
     const int n = blockIdx.x / (xblocks * yblocks);
     const int x0 = xb * IM2COL_PX, y0 = yb * IM2COL_ROWS;
-    for (int i = threadIdx.x; i < Cin * TR * (IM2COL_PX + 2); i += blockDim.x) {
-        const int col = i % (IM2COL_PX + 2);
-        const int row = i / (IM2COL_PX + 2);  // c * TR + r
-        const int c = row / TR, r = row % TR;
-        const int yy = y0 + r - 1, xx = x0 + col - 1;
-        float v = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * Cin + c) * H + yy) * W + xx);
-        tile[row][col] = v;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // stage: one warp per (channel, row) line, lanes stride over the columns (no div / mod per element)
+    for (int row = warp; row < Cin * TR; row += 8) {
+        const int c = row / TR, r = row % TR;   // compile-time divisors
+        const int yy = y0 + r - 1;
+        const bool row_ok = yy >= 0 && yy < H;
+        const float* src = x + (((size_t)n * Cin + c) * H + (row_ok ? yy : 0)) * W;
+#pragma unroll
+        for (int t = 0; t < (PITCH + 31) / 32; ++t) {
+            const int col = lane + 32 * t;
+            const int xx = x0 + col - 1;
+            if (col < PITCH) tile[row * PITCH + col] = (row_ok && xx >= 0 && xx < W) ? __ldg(src + xx) : 0.f;
+        }
     }
+    if (threadIdx.x == 0) tile[ZERO] = 0.f;
     __syncthreads();
+    // gather: a thread always emits the same 16-byte chunk g (8 consecutive k) of its pixels, so the eight
+    // shared-memory offsets of that chunk are loop invariants
+    const int g = threadIdx.x & 7;
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = g * 8 + j;
+        const int tap = k / Cin, c = k % Cin;
+        off[j] = k < K ? (c * TR + tap / 3) * PITCH + tap % 3 : -1;
+    }
     const int npx = min(IM2COL_PX, W - x0);
     const int nrows = min(IM2COL_ROWS, H - y0);
-    for (int i = threadIdx.x; i < nrows * npx * 8; i += blockDim.x) {
-        const int g = i & 7, px = (i >> 3) % npx, ry = (i >> 3) / npx;
-        float f[8];
+    for (int ry = 0; ry < nrows; ++ry) {
+        bf16* orow = out + (((size_t)n * H + y0 + ry) * W + x0) * 64 + g * 8;
+        for (int px = threadIdx.x >> 3; px < npx; px += 32) {
+            const int base = ry * PITCH + px;
+            float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float v = 0.f;
-            if (k < K) {
-                const int tap = k / Cin, c = k % Cin;
-                v = tile[c * TR + ry + tap / 3][px + tap % 3];
-            }
-            f[j] = v;
+            for (int j = 0; j < 8; ++j) f[j] = tile[off[j] >= 0 ? off[j] + base : ZERO];
+            *reinterpret_cast<uint4*>(orow + (size_t)px * 64) = pack8(f);
         }
-        const size_t pix = ((size_t)n * H + y0 + ry) * W + x0 + px;
-        *reinterpret_cast<uint4*>(out + pix * 64 + g * 8) = pack8(f);
     }
 }
 
