@@ -118,11 +118,32 @@ def run_reference(args):
 
 # --------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~5 ms, in a thread;
+    falls back to an `nvidia-smi -lms` child process when pynvml is missing)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.samples, self.stop_flag = [], None, None, [], False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -132,11 +153,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = [m for m, _ in self.samples]
+            reasons = set()
+            for _, mask in self.samples:
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -158,7 +201,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------- GPU arm

@@ -587,7 +587,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     if (tr_on < 0) { const char* e = getenv("SDN_WGRAD_TR"); tr_on = e ? atoi(e) : 1; }
     // measured: the swapped roles win when a unit is 64 channels wide or when there are >= 6 units
     // (two sources); 3 units of 32 channels are issue-bound either way and stay in the plain layout
-    p.tr = (tr_on && p.halo && (cout == 32 || cout == 64) && (CA == 64 || 3 * (cin_tot / CA) >= 6)) ? 1 : 0;
+    p.tr = (tr_on && p.halo && (cout == 32 || cout == 64) && (tr_on == 2 || CA == 64 || 3 * (cin_tot / CA) >= 6)) ? 1 : 0;
     for (size_t i = 0; i < avariants.size(); ++i) {
         const SrcView& v = avariants[i];
         if (p.tr) SDN_OK(encode4(&p.a_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, cout, t.TW, t.TH, t.TN, cout * 2));
@@ -1016,6 +1016,9 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
         SDN_OK(bn_backward(c, L, B, st));
     }
     {
+        static int wdbg_layer = -2;
+        if (wdbg_layer == -2) { const char* e = getenv("SDN_DEBUG_TRACE_WGRAD"); wdbg_layer = e ? atoi(e) : -1; }
+        L.wgrad.p.dbg = (i == wdbg_layer) ? c->dbg : nullptr;
         ProfScope ps(c, st, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
         SDN_OK(launch_wg(c, L.wgrad, st));
     }

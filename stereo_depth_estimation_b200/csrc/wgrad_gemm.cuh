@@ -51,7 +51,18 @@ struct alignas(64) WgradParams {
     int k_rows_valid;       // rows of the workspace that exist
     float* out;             // [a_variants][taps * cin_tot][cout] fp32, pre-zeroed
     int tr;                 // transposed roles (Cout <= 64, 3x3): M = (vertical tap, ci) rows of a unit, N = co
+    long long* dbg;         // -DSDN_FORENSICS: clock64 stamps [role][tile < 16][event < 8] of CTA (0,0,0)
 };
+
+#ifdef SDN_FORENSICS
+#define SDN_WDBG(role, tile, ev)                                                                          \
+    do {                                                                                                  \
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 16)      \
+            p.dbg[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                                          \
+    } while (0)
+#else
+#define SDN_WDBG(role, tile, ev) do { } while (0)
+#endif
 
 // TR (Cout <= 64, 3x3 only): the roles are swapped.  The MMA's M side is one unit's halo tile - its three
 // row-shifted vertical taps are M-atoms LBO = TW rows apart, M = 128 = 4 x 32 channels (the 4th atom is
@@ -126,9 +137,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                 u_dx[g] = dxi - 1;
             }
             ptx::TileWalker tw;
+            int dbg_it = 0;
             for (tw.init(blockIdx.x, gridDim.x, ptiles, 1, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
                 const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
+                const int dbg_tile = dbg_it++;
+                (void)dbg_tile;
+                if (lane == 0) SDN_WDBG(0, dbg_tile, 0);
                 ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                if (lane == 0) SDN_WDBG(0, dbg_tile, 1);
                 uint8_t* a_dst = smem + s * stage_bytes;
                 uint8_t* b_dst = a_dst + p.a_atoms * a_tile_bytes;
                 if (ptx::elect_one()) {
@@ -143,6 +159,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                                              x0 + u_dx[g], y0 - (HALO ? 1 : 0), n0);
                 }
                 __syncwarp();
+                if (lane == 0) SDN_WDBG(0, dbg_tile, 2);
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
@@ -175,8 +192,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
             const uint32_t tr_dy2_16 = uint32_t(2 * p.TW * SWB) >> 4;
             const int nmma = grouped ? 1 : nunits;
             for (int it = 0; it < my_tiles; ++it) {
+                if (lane == 0) SDN_WDBG(1, it, 0);
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
+                if (lane == 0) SDN_WDBG(1, it, 1);
                 const uint64_t sa = adesc0 + uint64_t(s * stage16);
                 const uint64_t sb = bdesc0 + uint64_t(s * stage16);
                 // one election per stage.  Where it measured faster (32-channel swapped-role units, the deep
@@ -224,8 +243,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                         }
                     }
                 }
+                if (lane == 0) SDN_WDBG(1, it, 2);
                 if (leader) ptx::tc_commit(&empty_bar[s]);
                 __syncwarp();
+                if (lane == 0) SDN_WDBG(1, it, 3);
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
             if (ptx::elect_one()) ptx::tc_commit(tfull_bar);

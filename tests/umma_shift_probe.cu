@@ -84,6 +84,87 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     if (warp == 0) ptx::tmem_dealloc(tmem, 64);
 }
 
+// ---- second probe: cost of back-to-back MMAs into the SAME accumulator vs several accumulators ----
+// 64 MMAs (M = 128, K = 16, operands = whatever is in shared memory) issued by one thread; nacc
+// accumulators used round-robin; cycles from first issue to the commit's mbarrier arrival.
+template <int N, int NACC, int MODE>
+__global__ void __launch_bounds__(128, 1) chain_kernel(long long* out, int slot) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 64 * 1024);
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 16 * 1024; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { ptx::mbar_init(&bars[0], 1); ptx::fence_mbar_init(); }
+    if (warp == 0) { ptx::tmem_alloc(tptr, 512); ptx::tmem_relinquish(); }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tptr;
+    if (MODE >= 2 ? warp == 0 : threadIdx.x == 0) {
+        constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, N, 0, 0);
+        const uint64_t adesc = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, 2u);
+        const uint64_t bdesc = ptx::make_smem_desc(ptx::smem_u32(smem) + 32 * 1024, 16, 1024, 2u);
+        uint32_t ph = 0;
+        const uint32_t lead = (MODE >= 2) ? (ptx::elect_one() ? 1u : 0u) : 1u;
+        for (int rep = 0; rep < 3; ++rep) {
+            const long long t0 = clock64();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                if (MODE == 0)
+                    ptx::tc_mma_bf16(tmem + uint32_t((i % NACC) * N), adesc + uint64_t(2 * (i & 3)), bdesc + uint64_t(2 * (i & 3)),
+                                     IDESC, 1u);
+                else if (MODE == 1)
+                    ptx::tc_mma_bf16(tmem, adesc, bdesc, IDESC, 1u);
+                else if (MODE == 2)
+                    ptx::tc_mma_bf16_pred(tmem + uint32_t((i % NACC) * N), adesc + uint64_t(2 * (i & 3) + 64 * (i >> 2 & 3)),
+                                          bdesc + uint64_t(2 * (i & 3)), IDESC, 1u, lead);
+                else {
+                    // MN-major operands (wgrad): MODE 3 = 64-byte swizzle atoms (32 channels), MODE 4 = 128-byte
+                    constexpr uint32_t SW = MODE == 3 ? 64 : 128;
+                    constexpr uint32_t LAY = MODE == 3 ? 4u : 2u;
+                    constexpr uint32_t ID = ptx::make_idesc_bf16(128, N, 1, 1);
+                    const uint64_t am = ptx::make_smem_desc(ptx::smem_u32(smem), 8 * SW, 8 * SW, LAY);
+                    const uint64_t bm = ptx::make_smem_desc(ptx::smem_u32(smem) + 32 * 1024, 16 * SW, 8 * SW, LAY);
+                    ptx::tc_mma_bf16_pred(tmem + uint32_t((i % NACC) * N), am + uint64_t((16 * SW / 16) * (i & 3)),
+                                          bm + uint64_t((16 * SW / 16) * (i & 3)), ID, 1u, lead);
+                }
+            }
+            const long long t1 = clock64();
+            if (lead) ptx::tc_commit(&bars[0]);
+            ptx::mbar_wait(&bars[0], ph);
+            ph ^= 1;
+            const long long t2 = clock64();
+            if (rep == 2 && lead) { out[slot * 2] = t1 - t0; out[slot * 2 + 1] = t2 - t0; }
+            if (MODE >= 2) __syncwarp();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+template <int N, int NACC, int MODE>
+static void run_chain1(long long* dout, int& slot) {
+    const int smem = 1024 + 64 * 1024 + 256;
+    cudaFuncSetAttribute(chain_kernel<N, NACC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    chain_kernel<N, NACC, MODE><<<1, 128, smem>>>(dout, slot);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[2] = {0, 0};
+    cudaMemcpy(h, dout + slot * 2, sizeof h, cudaMemcpyDeviceToHost);
+    printf("chain mode=%d N=%d accumulators=%d : issue %lld cyc, done %lld cyc -> %.1f cyc/MMA (%s)\n", MODE, N, NACC, h[0], h[1],
+           h[1] / 64.0, cudaGetErrorString(e));
+    ++slot;
+}
+template <int N>
+static void run_chain(long long* dout, int& slot) {
+    run_chain1<N, 1, 2>(dout, slot);
+    run_chain1<N, 2, 3>(dout, slot);
+    run_chain1<N, 2, 4>(dout, slot);
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -160,7 +241,15 @@ int main() {
         return 1;
     }
     EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
-    int rc = run<128>(enc);
-    rc |= run<64>(enc);
+    int rc = 0;
+    if (getenv("PROBE_SHIFT") != nullptr) { rc = run<128>(enc); rc |= run<64>(enc); }
+    long long* dout;
+    cudaMalloc(&dout, 64 * 2 * sizeof(long long));
+    int slot = 0;
+    run_chain<32>(dout, slot);
+    run_chain<64>(dout, slot);
+    run_chain<128>(dout, slot);
+    run_chain<96>(dout, slot);
+    run_chain<256>(dout, slot);
     return rc;
 }
