@@ -128,6 +128,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
     constexpr uint32_t SBO_A = 8 * SWA;
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BLOCK_N, 0, 0);
 
+    ptx::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
@@ -179,6 +180,8 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    ptx::pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer

@@ -115,6 +115,7 @@ struct PackTable {
     int total;
 };
 __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackTable t) {
+    SDN_PDL_ENTRY();
     __shared__ int starts[53];
     if (threadIdx.x <= t.n) starts[threadIdx.x] = threadIdx.x < t.n ? t.e[threadIdx.x].start : t.total;
     __syncthreads();
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ P
 
 // bias replicated over the 4 quadrants of a ConvTranspose2d GEMM: dst[q*Co + co] = b[co]
 __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int Co, int reps) {
+    SDN_PDL_ENTRY();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Co * reps; i += gridDim.x * blockDim.x) dst[i] = b[i % Co];
 }
 
@@ -150,6 +152,7 @@ constexpr int IM2COL_MAXC = 8;
 template <int Cin>
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
                                                            int H, int W) {
+    SDN_PDL_ENTRY();
     // +1: one always-zero cell that the k >= 9*Cin padding lanes read (branch-free gather)
     __shared__ float tile[Cin * (IM2COL_ROWS + 2) * (IM2COL_PX + 2) + 1];
     static_assert(Cin <= IM2COL_MAXC, "first-layer channel count");
@@ -214,6 +217,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
                                          long long* __restrict__ num_batches, float eps, float momentum,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    SDN_PDL_ENTRY();
     // one warp per channel: lanes stride over the partial rows, fixed-shape butterfly -> deterministic
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -249,6 +253,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
 __global__ void bn_prepare_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                        float eps, float* __restrict__ scale, float* __restrict__ shift) {
+    SDN_PDL_ENTRY();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float rstd = 1.f / sqrtf(running_var[c] + eps);
@@ -263,6 +268,7 @@ template <bool POOL>
 __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                                     const float* __restrict__ shift, bf16* __restrict__ a, bf16* __restrict__ pooled,
                                     unsigned short* __restrict__ amax, int B, int H, int W, int C) {
+    SDN_PDL_ENTRY();
     const int CG = C >> 3;
     if (POOL) {
         const int H2 = H >> 1, W2 = W >> 1;
@@ -319,6 +325,7 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
 
 // 2x2 max pool of an NHWC bf16 tensor (eval path: BN+ReLU already applied by the conv epilogue).
 __global__ void maxpool2x2_kernel(const bf16* __restrict__ a, bf16* __restrict__ pooled, int B, int H, int W, int C) {
+    SDN_PDL_ENTRY();
     const int CG = C >> 3, H2 = H >> 1, W2 = W >> 1;
     const long long total = (long long)B * H2 * W2 * CG;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -421,6 +428,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
                                                             float* __restrict__ partials, int B, int H, int W, int C) {
+    SDN_PDL_ENTRY();
     const int CG = C >> 3;
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,6 +458,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate) {
+    SDN_PDL_ENTRY();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -481,6 +490,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const b
                                                            const float* __restrict__ rstd,
                                                            const float* __restrict__ c1, const float* __restrict__ c2,
                                                            bf16* __restrict__ dy, int B, int H, int W, int C) {
+    SDN_PDL_ENTRY();
     const int CG = C >> 3;
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const b
 // Per-channel column sum of an NHWC bf16 tensor (ConvTranspose2d bias gradient).
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long npix, int C,
                                                      float* __restrict__ out, int accumulate) {
+    SDN_PDL_ENTRY();
     // one block per 8-channel group slice; grid.x = C/8, grid.y = slices (atomics merge slices)
     const int cg = blockIdx.x;
     float s[8];
@@ -549,6 +560,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
                                                    unsigned long long* __restrict__ count_out,
                                                    bf16* __restrict__ g_d1, float* __restrict__ head_grads,
                                                    long long npix) {
+    SDN_PDL_ENTRY();
     __shared__ float swd[32], swl[32];
     __shared__ float red[8][72];
     if (threadIdx.x < 32) { swd[threadIdx.x] = w_d[threadIdx.x]; swl[threadIdx.x] = w_l[threadIdx.x]; }
@@ -646,6 +658,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
 __global__ void __launch_bounds__(256) mask_count_kernel(const float* __restrict__ target,
                                                          const uint8_t* __restrict__ mask, long long npix,
                                                          unsigned long long* __restrict__ n_out) {
+    SDN_PDL_ENTRY();
     unsigned int c = 0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
          p += (long long)gridDim.x * blockDim.x)
@@ -675,6 +688,7 @@ struct AdamTable {
     int n;
 };
 __global__ void adamw_step_count_kernel(long long* step_dev, const unsigned long long* gate) {
+    SDN_PDL_ENTRY();
     if (gate == nullptr || *gate != 0ull) *step_dev += 1;
 }
 __global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ AdamTable t, double lr, double beta1,
@@ -682,6 +696,7 @@ __global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ 
                                                         float eps, float decay,
                                                         const long long* __restrict__ step_dev,
                                                         const unsigned long long* __restrict__ gate) {
+    SDN_PDL_ENTRY();
     if (gate != nullptr && *gate == 0ull) return;
     __shared__ int starts[67];
     if (threadIdx.x <= t.n) starts[threadIdx.x] = t.start[threadIdx.x];
@@ -716,6 +731,7 @@ __global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ 
 // mode 3: convT     ws[q][ci][Co]          -> grad[Ci][Co][2][2]
 __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int mode, int Co, int Ci,
                                    int accumulate) {
+    SDN_PDL_ENTRY();
     const int total = (mode == 3) ? 4 * Co * Ci : 9 * Co * Ci;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v;
@@ -733,9 +749,11 @@ __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restri
 // Zero fills as kernels: cudaMemsetAsync may be served by a copy engine, where it would queue behind a
 // bulk host->device prefetch running on another stream.
 __global__ void zero_u64_kernel(unsigned long long* __restrict__ p, int n) {
+    SDN_PDL_ENTRY();
     for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0ull;
 }
 __global__ void __launch_bounds__(256) zero_u32_kernel(uint32_t* __restrict__ p, size_t n) {
+    SDN_PDL_ENTRY();
     const size_t n4 = n / 4;
     uint4* p4 = reinterpret_cast<uint4*>(p);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x)
@@ -743,6 +761,7 @@ __global__ void __launch_bounds__(256) zero_u32_kernel(uint32_t* __restrict__ p,
     for (size_t i = n4 * 4 + blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = 0u;
 }
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int accumulate) {
+    SDN_PDL_ENTRY();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (accumulate) dst[i] += src[i]; else dst[i] = src[i];
     }

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
     int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
     unsigned long long* __restrict__ valid_count, const AugParams* __restrict__ aug, float* __restrict__ gray_part,
     int parts_per_view) {
+    SDN_PDL_ENTRY();
     const int n = blockIdx.y;
     const int xblocks = (W + 127) / 128;
     const int xb = blockIdx.x % xblocks;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(256) decode_resize_smem_kernel(
     int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
     unsigned long long* __restrict__ valid_count, const AugParams* __restrict__ aug, float* __restrict__ gray_part,
     int parts_per_view, int max_rows, int row_bytes) {
+    SDN_PDL_ENTRY();
     extern __shared__ __align__(16) uint8_t sm[];
     // u8 -> float / 255 as a table of the 256 correctly-rounded quotients: bit-identical to the
     // reference's float32 division (dataset.py:185) at a fraction of the instruction count
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(256) augment_point_kernel(float* __restrict__ 
                                                             const AugParams* __restrict__ aug,
                                                             const float* __restrict__ gray_part, int parts_per_view,
                                                             float* __restrict__ blur_tmp) {
+    SDN_PDL_ENTRY();
     const int view = blockIdx.y;  // 2*n + {0: left, 1: right}
     const AugParams a = aug[view];
     __shared__ float s_mean;
@@ -436,6 +439,7 @@ template <int KS>
 __global__ void __launch_bounds__(256) blur_noise_kernel(float* __restrict__ input, int B, int H, int W,
                                                          const AugParams* __restrict__ aug,
                                                          const float* __restrict__ blur_tmp) {
+    SDN_PDL_ENTRY();
     const int view = blockIdx.z;
     const AugParams a = aug[view];
     if (!(a.blur_sigma > 0.f)) return;

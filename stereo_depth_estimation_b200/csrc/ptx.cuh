@@ -216,6 +216,13 @@ struct TileWalker {
     }
 };
 
+// Programmatic dependent launch: let the next kernel in the stream start launching (its blocks are
+// scheduled as SM resources free up and park at their own pdl_wait), and block until every kernel
+// before this one has completed and flushed its writes.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define SDN_PDL_ENTRY() do { sdn::ptx::pdl_launch_dependents(); sdn::ptx::pdl_wait(); } while (0)
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

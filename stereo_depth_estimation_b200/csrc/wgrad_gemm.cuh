@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     constexpr int CA = SWB / 2;  // channels per B atom
     constexpr uint32_t LAYOUT_B = (SWB == 128) ? 2u : 4u;
 
+    ptx::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    ptx::pdl_wait();
 
     const int my_tiles = (int)blockIdx.x < ptiles ? (ptiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
