@@ -94,6 +94,12 @@ struct CgCfg {
     // their main loop): two epilogue warpgroups, one per TMEM accumulator stage, take alternate tiles
     static constexpr int EG = BLOCK_N <= 64 ? 2 : 1;
     static constexpr int THREADS = 64 + 128 * EG;
+    // N = 32: BatchNorm statistics accumulate in registers (64 per epilogue thread); wider tiles would spill
+#ifdef SDN_NO_REGSTATS
+    static constexpr bool REGSTATS = false;
+#else
+    static constexpr bool REGSTATS = BLOCK_N == 32;
+#endif
     static constexpr int SCRATCH_BYTES = EG * RG * BLOCK_N * 2 * 4;
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
@@ -360,6 +366,12 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
             for (int j = 0; j < Cfg::D_BLOCKS; ++j)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) st_acc[i][j][k] = 0.f;
+        // N = 32: statistics stay in REGISTERS - this thread's row, every channel - across all of
+        // its tiles; no shared-memory pass per tile.  (N >= 128 keeps the column-slice pass below.)
+        constexpr int RSN = Cfg::REGSTATS ? BLOCK_N : 1;
+        float rs[RSN], rq[RSN];
+#pragma unroll
+        for (int j = 0; j < RSN; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
         int sbuf = 0;
         int dbg_it = 0;
         const int dmap_div = p.n_per_dmap;   // channels per destination map
@@ -422,6 +434,17 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                     q.w = ptx::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
                     const int sw = (Cfg::SWD == 128) ? ((j0 + i) ^ (r & 7)) : ((j0 + i) ^ ((r >> 1) & 3));
                     *reinterpret_cast<uint4*>(rowp + (sw << 4)) = q;
+                    if (Cfg::REGSTATS && do_stats) {
+                        // sums of the bf16-ROUNDED values (what the next kernel reads back)
+                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float lo = __uint_as_float(w4[h] << 16), hi = __uint_as_float(w4[h] & 0xFFFF0000u);
+                            const int c = Cfg::REGSTATS ? ch * 32 + 8 * i + 2 * h : 0;
+                            rs[c % RSN] += lo; rq[c % RSN] = fmaf(lo, lo, rq[c % RSN]);
+                            rs[(c + 1) % RSN] += hi; rq[(c + 1) % RSN] = fmaf(hi, hi, rq[(c + 1) % RSN]);
+                        }
+                    }
                 }
             }
             // accumulator drained: hand the TMEM stage back to the MMA warp
@@ -446,7 +469,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                 ptx::tma_store_commit();
             }
             if (dbg_lead) SDN_DBG(2, dbg_tile, 6);
-            if (do_stats) {
+            if (!Cfg::REGSTATS && do_stats) {
                 // per-channel sum / sum of squares of the bf16 values just staged (== what the
                 // next kernel reads back).  Each thread owns one 32-bit word column (2 channels)
                 // of one row group and keeps its partials in REGISTERS across tiles; the
@@ -484,7 +507,28 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                 if (a == 0) aph ^= 1;
             }
         }
-        if (do_stats) {
+        if (Cfg::REGSTATS && do_stats) {
+            // one reduction per kernel: 32 rows by warp shuffle, the group's 4 warps through scratch
+            float* dst = p.stats_partials + size_t(blockIdx.x * EG + eg) * 2 * p.n_total;
+            scratch += eg * (Cfg::SCRATCH_BYTES / 4 / EG);
+            const int wq = (threadIdx.x >> 5) & 3;
+#pragma unroll
+            for (int c = 0; c < RSN; ++c) {
+                float a = rs[c], b = rq[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) { scratch[wq * 2 * BLOCK_N + c] = a; scratch[wq * 2 * BLOCK_N + BLOCK_N + c] = b; }
+            }
+            ptx::named_bar_sync(3 + eg, 128);
+            for (int o = te; o < 2 * BLOCK_N; o += 128) {
+                const float v = (scratch[o] + scratch[2 * BLOCK_N + o]) + (scratch[4 * BLOCK_N + o] + scratch[6 * BLOCK_N + o]);
+                const int kind = o / BLOCK_N, c = o % BLOCK_N;
+                if (c < p.n_total) dst[kind * p.n_total + c] = v;
+            }
+        } else if (do_stats) {
             // one cross-row-group reduction per kernel: scratch[rg][channel] -> per-CTA partials
             float* dst = p.stats_partials + size_t(blockIdx.x * EG + eg) * 2 * p.n_total;
             scratch += eg * (Cfg::SCRATCH_BYTES / 4 / EG);

@@ -23,6 +23,7 @@
 #include "elementwise.cuh"
 #include "preprocess.cuh"
 #include "wgrad_gemm.cuh"
+#include "wgrad_tr.cuh"
 
 using namespace sdn;
 
@@ -152,6 +153,7 @@ struct GemmOp {
 };
 struct WgradOp {
     WgradParams p;
+    int tr2_natoms = 0;   // > 0: wgrad_tr_kernel<CA, Cout, natoms> (3x3, Cout <= 64)
     int swb = 128, smem = 0;
     dim3 grid;
 };
@@ -334,6 +336,18 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     return fail("no conv_gemm instantiation for swizzle %d, BLOCK_N %d", op.swa, op.block_n);
 }
 static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
+    if (op.tr2_natoms > 0) {
+        const int ca = op.swb / 2;
+        if (ca == 32 && op.p.cout == 32 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<32, 32, 1>, op.grid, 192, op.smem, st, op.p);
+        else if (ca == 32 && op.p.cout == 32 && op.tr2_natoms == 2) launch_k(wgrad_tr_kernel<32, 32, 2>, op.grid, 192, op.smem, st, op.p);
+        else if (ca == 32 && op.p.cout == 64 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<32, 64, 1>, op.grid, 192, op.smem, st, op.p);
+        else if (ca == 64 && op.p.cout == 64 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<64, 64, 1>, op.grid, 192, op.smem, st, op.p);
+        else if (ca == 64 && op.p.cout == 32 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<64, 32, 1>, op.grid, 192, op.smem, st, op.p);
+        else return fail("no wgrad_tr instantiation for CA %d, Cout %d, atoms %d", ca, op.p.cout, op.tr2_natoms);
+        ++c->launches;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (op.swb == 128) {
         if (op.p.tr) launch_k(wgrad_gemm_kernel<128, true, true>, op.grid, 192, op.smem, st, op.p);
         else if (op.p.halo) launch_k(wgrad_gemm_kernel<128, true>, op.grid, 192, op.smem, st, op.p);
@@ -362,6 +376,11 @@ static int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<128, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<64, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 32, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 32, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<64, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<64, 32, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
 }
 
@@ -583,6 +602,41 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     const int CA = op.swb / 2;
     const int W = avariants[0].W, H = avariants[0].H;
     p.halo = taps == 9 ? 1 : 0;
+    op.tr2_natoms = 0;
+    static int tr2_on = -1;
+    if (tr2_on < 0) { const char* e = getenv("SDN_WGRAD_TR2"); tr2_on = e ? atoi(e) : 1; }
+    if (tr2_on && p.halo && (cout == 32 || cout == 64) && W % 8 == 0 && avariants.size() == 1 && avariants[0].C == cout) {
+        // levels 1-2 (small Cout, many pixels): swapped roles, one halo box per channel atom (wgrad_tr.cuh)
+        const int atoms = cin_tot / CA;
+        const int natoms = CA == 32 ? std::min(atoms, 2) : 1;
+        const SrcView& y = avariants[0];
+        SDN_OK(encode4(&p.a_maps[0], y.base, y.C, y.W, y.H, B, y.sW, y.sH, y.sN, cout, 8, 16, 1, cout * 2));
+        for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+        for (size_t i = 0; i < bsrc.size(); ++i) {
+            const SrcView& v = bsrc[i];
+            SDN_OK(encode4(&p.b_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, CA, 10, 18, 1, op.swb));
+        }
+        if (bsrc.size() == 1) p.b_maps[1] = p.b_maps[0];
+        p.TW = 8; p.TH = 16; p.TN = 1; p.kpix = 128;
+        p.tiles_x = W / 8; p.tiles_y = (H + 15) / 16; p.tiles_n = B;
+        p.atoms_per_tap = atoms;
+        p.atoms_src0 = bsrc[0].C / CA;
+        p.unit_groups = (atoms + natoms - 1) / natoms;
+        p.cout = cout; p.cin_tot = cin_tot; p.k_rows_valid = k_rows_valid; p.out = out; p.tr = 2;
+        const int y_bytes = 128 * cout * 2;
+        const int x_bytes = (10 * 18 * op.swb + 1023) & ~1023;
+        const int stage_bytes = y_bytes + natoms * x_bytes;
+        const int fixed = 1024 + 4 * 32 * 33 * 4 + 256;
+        p.stages = std::max(2, std::min(8, (220 * 1024 - fixed) / stage_bytes));
+        op.smem = fixed + p.stages * stage_bytes;
+        op.tr2_natoms = natoms;
+        const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
+        static int waves2 = -1;
+        if (waves2 < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves2 = e ? atoi(e) : 2; }
+        int split = std::max(1, std::min((waves2 * c->num_sms) / p.unit_groups, ptiles));
+        op.grid = dim3(split, p.unit_groups, 1);
+        return 0;
+    }
     Tile t;
     if (p.halo) {
         // one image per box, TW a multiple of 8 (row shifts must be whole swizzle groups)

@@ -224,12 +224,29 @@ __global__ void __launch_bounds__(256) decode_resize_smem_kernel(
     const int byte0 = (col_first * 3) & ~15;                       // 16-byte aligned inside the row
     const int byte1 = min(((col_last + 1) * 3 + 15) & ~15, Ws * 3);
     const int chunks = (byte1 - byte0) >> 4;
-    for (int i = threadIdx.x; i < 3 * nrows * chunks; i += blockDim.x) {
-        const int ck = i % chunks;
-        const int rr = (i / chunks) % nrows;
-        const int im = i / (chunks * nrows);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(srcs[im] + (size_t)(row_first + rr) * Ws * 3 + byte0) + ck);
-        *reinterpret_cast<uint4*>(sm + ((size_t)(im * max_rows + rr) * row_bytes) + (ck << 4)) = v;
+    {
+        // one warp per (image, source row) line, lanes over its 16-byte chunks: no div / mod per chunk and
+        // up to four independent 128-bit loads in flight per thread
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const size_t pitch = (size_t)Ws * 3;
+        for (int line = warp; line < 3 * nrows; line += 8) {
+            const int im = line >= 2 * nrows ? 2 : (line >= nrows ? 1 : 0);
+            const int rr = line - im * nrows;
+            const uint4* src = reinterpret_cast<const uint4*>(srcs[im] + (size_t)(row_first + rr) * pitch + byte0);
+            uint4* dst = reinterpret_cast<uint4*>(sm + (size_t)(im * max_rows + rr) * row_bytes);
+            uint4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int ck = lane + 32 * t;
+                if (ck < chunks) v[t] = __ldg(src + ck);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int ck = lane + 32 * t;
+                if (ck < chunks) dst[ck] = v[t];
+            }
+            for (int ck = lane + 128; ck < chunks; ck += 32) dst[ck] = __ldg(src + ck);   // wider-than-usual rows
+        }
     }
     __syncthreads();
 
