@@ -505,6 +505,20 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const b
         bn_bwd_item<POOL, true>(y, g, gp, amax, sc, sh, mu, rs, k1, k2, i, H, W, C, s1, s2, dy);
 }
 
+// ConvTranspose2d bias gradient from the per-CTA column sums that the producing dgrad's epilogue
+// already wrote (CG_STATS partial rows [nparts][2 * n_total], sums first): one warp per channel.
+__global__ void colsum_partials_kernel(const float* __restrict__ partials, int nparts, int n_total, int C,
+                                       float* __restrict__ out) {
+    SDN_PDL_ENTRY();
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = lane; i < nparts; i += 32) s += (double)partials[(size_t)i * 2 * n_total + c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = (float)s;
+}
+
 // Per-channel column sum of an NHWC bf16 tensor (ConvTranspose2d bias gradient).
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long npix, int C,
                                                      float* __restrict__ out, int accumulate) {

@@ -186,6 +186,7 @@ struct UpL {  // ConvTranspose2d(k=2, s=2)
     float* bg = nullptr;  // [cout]
     GemmOp fprop, dgrad;
     WgradOp wgrad;
+    bool bias_fused = false;  // bias gradient comes from the column sums of the dgrad that writes `gu`
 };
 
 struct sdn_ctx {
@@ -872,6 +873,13 @@ static int prepare_batch(sdn_ctx* c, int B) {
                 dv.push_back(full_view(c->conv[i - 1].gp));
             }
             SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr, true));
+            if (L.nsrc == 2) {
+                // the first destination is the up-conv output gradient: its per-channel column sums are the
+                // ConvTranspose2d bias gradient, and the epilogue can produce them like BatchNorm statistics
+                UpL& U = c->up[(i - 10) / 2];
+                U.bias_fused = L.dgrad.p.n_tiles == 1 && L.dgrad.block_n <= 128;
+                if (U.bias_fused) { L.dgrad.p.flags |= CG_STATS; L.dgrad.p.stats_partials = c->stats_partials; }
+            }
         }
         // ---- weight gradient
         std::vector<SrcView> bs;
@@ -1108,6 +1116,12 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
         ++c->launches;
     }
     if (L.has_dgrad) SDN_OK(launch_cg(c, L.dgrad, st));
+    if (L.has_dgrad && L.nsrc == 2 && c->up[(i - 10) / 2].bias_fused) {
+        UpL& U = c->up[(i - 10) / 2];
+        launch_k(colsum_partials_kernel, (U.cout * 32 + 255) / 256, 256, 0, st, c->stats_partials,
+                 L.dgrad.grid * (L.dgrad.block_n <= 64 ? 2 : 1), L.dgrad.p.n_total, U.cout, U.bg);
+        ++c->launches;
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1117,7 +1131,7 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
     const long long npix = (long long)B * U.gu.H * U.gu.W;
     dim3 g(U.cout / 8, (unsigned)std::max(1LL, std::min((npix + 255) / 256, (long long)(c->num_sms * 2))));
     const double pxin = (double)B * U.src->H * U.src->W;
-    {
+    if (!U.bias_fused) {
         ProfScope ps(c, st, "convT_bias_grad", 100 + k, 0.0, (double)npix * U.cout * 2);
         launch_k(colsum_kernel, g, 256, 0, st, U.gu.p, npix, U.cout, U.bg, 0);
         ++c->launches;
