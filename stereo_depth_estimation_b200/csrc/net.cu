@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/sdn.h"
@@ -903,10 +904,23 @@ static int prepare_batch(sdn_ctx* c, int B) {
     return 0;
 }
 
-static inline int ew_grid(const sdn_ctx* c, long long work_items, int block) {
-    long long need = (work_items + block - 1) / block;
-    long long cap = (long long)c->num_sms * 8;
-    return (int)std::max(1LL, std::min(need, cap));
+// Grid of a grid-stride kernel = exactly the blocks that can be resident (occupancy x SMs): a larger grid
+// runs a partial last wave, and the tail of a 1.3-wave launch is a third of its time.
+template <typename K>
+static int occ_grid(const sdn_ctx* c, K kernel, long long work_items, int block) {
+    static std::map<const void*, int> cache;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = cache.find(key);
+    int per_sm;
+    if (it == cache.end()) {
+        per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cache[key] = per_sm;
+    } else {
+        per_sm = it->second;
+    }
+    const long long need = (work_items + block - 1) / block;
+    return (int)std::max(1LL, std::min(need, (long long)c->num_sms * per_sm));
 }
 
 static int zero_fill(sdn_ctx* c, void* p, size_t bytes, cudaStream_t st) {
@@ -961,11 +975,11 @@ static int run_bn_relu(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     const int H = L.y.H, W = L.y.W, C = L.cout;
     if (L.pooled_out) {
         const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
-        launch_k(bn_relu_pool_kernel<true>, ew_grid(c, items, 256), 256, 0, st, L.y.p, L.scale, L.shift, L.a.p, L.pool.p,
+        launch_k(bn_relu_pool_kernel<true>, occ_grid(c, bn_relu_pool_kernel<true>, items, 256), 256, 0, st, L.y.p, L.scale, L.shift, L.a.p, L.pool.p,
                                                                          L.amax, B, H, W, C);
     } else {
         const long long items = (long long)B * H * W * (C / 8);
-        launch_k(bn_relu_pool_kernel<false>, ew_grid(c, items, 256), 256, 0, st, L.y.p, L.scale, L.shift, L.a.p, nullptr,
+        launch_k(bn_relu_pool_kernel<false>, occ_grid(c, bn_relu_pool_kernel<false>, items, 256), 256, 0, st, L.y.p, L.scale, L.shift, L.a.p, nullptr,
                                                                           nullptr, B, H, W, C);
     }
     ++c->launches;
@@ -1018,7 +1032,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             if (L.pooled_out) {
                 ProfScope ps(c, st, "maxpool", i, 0.0, px * L.cout * 2 * 1.25);
                 const long long items = (long long)B * (L.y.H / 2) * (L.y.W / 2) * (L.cout / 8);
-                launch_k(maxpool2x2_kernel, ew_grid(c, items, 256), 256, 0, st, L.a.p, L.pool.p, B, L.y.H, L.y.W, L.cout);
+                launch_k(maxpool2x2_kernel, occ_grid(c, maxpool2x2_kernel, items, 256), 256, 0, st, L.a.p, L.pool.p, B, L.y.H, L.y.W, L.cout);
                 ++c->launches;
             }
             continue;
@@ -1052,7 +1066,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     if (disp != nullptr) {
         const long long npix = (long long)B * H * W;
         ProfScope ps(c, st, "head_fwd", 0, 0.0, (double)npix * (64 + (logvar ? 8 : 4)));
-        launch_k(head_kernel<0>, ew_grid(c, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63],
+        launch_k(head_kernel<0>, occ_grid(c, head_kernel<0>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63],
                                                               c->params[64], c->params[65], disp, logvar, nullptr,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                               nullptr, nullptr, npix);
@@ -1069,7 +1083,8 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     const double count = (double)B * H * W;
     const bool pool = L.pooled_out;
     const long long items = pool ? (long long)B * (H / 2) * (W / 2) * (C / 8) : (long long)B * H * W * (C / 8);
-    int grid = (int)std::max(1LL, std::min((items + 255) / 256, (long long)BWD_BLOCKS));
+    int grid = pool ? occ_grid(c, bn_bwd_reduce_kernel<true>, items, 256) : occ_grid(c, bn_bwd_reduce_kernel<false>, items, 256);
+    grid = std::min(grid, BWD_BLOCKS);
     if (pool)
         launch_k(bn_bwd_reduce_kernel<true>, grid, 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd,
                                                          c->bwd_partials, B, H, W, C);
@@ -1080,12 +1095,11 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->bwd_partials, grid, C, count, L.c1, L.c2,
                                                             c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate);
     ++c->launches;
-    const int agrid = ew_grid(c, items, 256);
     if (pool)
-        launch_k(bn_bwd_apply_kernel<true>, agrid, 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd, L.c1,
+        launch_k(bn_bwd_apply_kernel<true>, occ_grid(c, bn_bwd_apply_kernel<true>, items, 256), 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd, L.c1,
                                                          L.c2, L.dy.p, B, H, W, C);
     else
-        launch_k(bn_bwd_apply_kernel<false>, agrid, 256, 0, st, L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
+        launch_k(bn_bwd_apply_kernel<false>, occ_grid(c, bn_bwd_apply_kernel<false>, items, 256), 256, 0, st, L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
                                                           L.c1, L.c2, L.dy.p, B, H, W, C);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
@@ -1111,7 +1125,7 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
                   L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
     if (c->grads[L.p_w] != nullptr) {
         const int n = 9 * L.cin * L.cout;
-        launch_k(unpack_grad_kernel, ew_grid(c, n, 256), 256, 0, st, L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
+        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, st, L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
                                                                c->accumulate);
         ++c->launches;
     }
@@ -1143,7 +1157,7 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
     ProfScope ps2(c, st, "convT_dgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
     if (c->grads[U.p_w] != nullptr) {
         const int n = 4 * U.cin * U.cout;
-        launch_k(unpack_grad_kernel, ew_grid(c, n, 256), 256, 0, st, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
+        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, st, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
         ++c->launches;
     }
     if (c->grads[U.p_b] != nullptr) {
@@ -1307,7 +1321,7 @@ int sdn_backward_begin(sdn_ctx* c, const float* g_disp, const float* g_logvar, i
     SDN_OK(backward_prologue(c, accumulate, st));
     const long long npix = (long long)c->B * c->H * c->W;
     ProfScope ps(c, st, "head_bwd", 0, 0.0, (double)npix * (64 + 8 + 64));
-    launch_k(head_kernel<1>, ew_grid(c, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+    launch_k(head_kernel<1>, occ_grid(c, head_kernel<1>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], nullptr, nullptr, g_disp, g_logvar, nullptr,
                                                           nullptr, nullptr, nullptr, nullptr, c->conv[17].ga.p,
                                                           c->head_grads, npix);
@@ -1324,7 +1338,7 @@ int sdn_count_valid(sdn_ctx* c, const float* target, const uint8_t* mask, int B,
     CUDA_OK(cudaSetDevice(c->device));
     SDN_OK(zero_fill(c, count_out, sizeof(unsigned long long), st));
     const long long npix = (long long)B * c->H * c->W;
-    launch_k(mask_count_kernel, ew_grid(c, npix, 256), 256, 0, st, target, mask, npix, count_out);
+    launch_k(mask_count_kernel, occ_grid(c, mask_count_kernel, npix, 256), 256, 0, st, target, mask, npix, count_out);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1352,7 +1366,7 @@ int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* 
     }
     // the gradient buffer of dec1's output doubles as scratch on the metrics-only path
     ProfScope ps(c, st, "head_loss", 0, 0.0, (double)npix * (64 + 4 + 1 + 64));
-    launch_k(head_kernel<2>, ew_grid(c, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+    launch_k(head_kernel<2>, occ_grid(c, head_kernel<2>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], disp, logvar, nullptr, nullptr, target, mask,
                                                           n_norm_dev, sums4, count, c->conv[17].ga.p, c->head_grads,
                                                           npix);
