@@ -379,13 +379,16 @@ def run_b200(args):
         achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         roof = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
-    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if any
+    # DRAM traffic per launch of that kernel family from the committed ncu --set full capture (profiles/)
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_wgrad_b256_summary.json")) as f:
+        src = "r1_ncu_full_step_b256_summary.json"
+        with open(os.path.join(ROOT, "profiles", src)) as f:
             cap = json.load(f)
-        if dname in ("conv_wgrad", "convT_wgrad") and b_local == 256:
-            roof["traffic"] = cap["dram_bytes_per_launch_avg"]
-            roof["traffic_source"] = "profiles/r1_ncu_wgrad_b256_summary.json (ncu --set full, dram__bytes_read+write per launch)"
+        if dname == "bn_bwd" and b_local == 256:
+            fam_cap = cap["families"]["bn_bwd"]
+            roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["layers_captured"]
+            roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the" \
+                                     " reduce + apply kernels, averaged over the 18 layers of one step)"
             roof["algorithmic_bytes_per_launch"] = d["bytes"] / max(d["calls"], 1)
     except Exception:
         pass
