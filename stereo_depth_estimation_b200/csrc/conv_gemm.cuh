@@ -93,7 +93,15 @@ struct CgCfg {
     // small-N tiles are epilogue-bound (the per-tile bookkeeping of a 128-thread epilogue is longer than
     // their main loop): two epilogue warpgroups, one per TMEM accumulator stage, take alternate tiles
     static constexpr int EG = BLOCK_N <= 64 ? 2 : 1;
-    static constexpr int THREADS = 64 + 128 * EG;
+    // -DSDN_TWO_MMA_WARPS: two MMA-issuing warps (one per TMEM stage / epilogue group), an experiment kept for
+    // reference: the pipe is not idle between tiles, so interleaving two tiles only delays both epilogues
+#ifdef SDN_TWO_MMA_WARPS
+    static constexpr int NMMA = EG;
+#else
+    static constexpr int NMMA = 1;   // measured: two issuing warps do not help (32->32 level 1: 11 % slower, 64->64: 5 % faster)
+#endif
+    static constexpr int EPI0 = 32 * (1 + NMMA);   // first epilogue thread
+    static constexpr int THREADS = EPI0 + 128 * EG;
     // N = 32: BatchNorm statistics accumulate in registers (64 per epilogue thread); wider tiles would spill
 #ifdef SDN_NO_REGSTATS
     static constexpr bool REGSTATS = false;
@@ -260,19 +268,33 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------- MMA issuer
+    } else if (warp <= Cfg::NMMA) {
+        // ---------------------------------------------------------- MMA issuer(s)
         // The whole warp runs the loop converged so the descriptor arithmetic stays in uniform
         // registers; only the tcgen05 instructions themselves are issued by one elected lane.
+        // NMMA == 2: warp 1 takes the even tiles of this CTA (TMEM stage 0), warp 2 the odd ones (stage 1).
         {
+            const int mw = warp - 1;
+            const int stages_per_tile = (p.kblocks_total + ups - 1) / ups;
+            // Two consumers are only safe while neither can run a whole ring ahead of the producer: an
+            // mbarrier parity wait two phases early returns true at once.  Both tiles' stages must fit.
+            const bool dual = Cfg::NMMA == 2 && 2 * stages_per_tile <= stages;
+            const int NMMA = dual ? 2 : 1;
             int s = 0;
             uint32_t ph = 0;
-            int a = 0;
+            int a = dual ? mw : 0;
             uint32_t aph = 0;
-            const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            if (!dual && mw != 0) my_tiles = 0;   // the second MMA warp idles
+            // skip the pipeline stages of the tiles the other MMA warp consumes
+            auto skip_stages = [&](int n) {
+                for (int i = 0; i < n; ++i)
+                    if (++s == stages) { s = 0; ph ^= 1; }
+            };
+            if (NMMA == 2) skip_stages(mw * stages_per_tile);
             if (bres) ptx::mbar_wait(bres_bar, 0);
             const uint32_t b_res_addr = ptx::smem_u32(b_res);
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int it = mw; it < my_tiles; it += NMMA) {
                 if (lane == 0) SDN_DBG(1, it, 0);
                 ptx::mbar_wait(&tempty_bar[a], aph ^ 1);
                 ptx::tc_fence_after();
@@ -339,16 +361,21 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_k
                 }
                 if (ptx::elect_one()) ptx::tc_commit(&tfull_bar[a]);
                 if (lane == 0) SDN_DBG(1, it, 7);
-                a ^= 1;
-                if (a == 0) aph ^= 1;
+                if (NMMA == 2) {
+                    aph ^= 1;
+                    skip_stages(stages_per_tile);
+                } else {
+                    a ^= 1;
+                    if (a == 0) aph ^= 1;
+                }
             }
         }
     } else {
         // ------------------------------------------------------------ epilogue
         constexpr int EG = Cfg::EG;
-        const int eg = EG == 2 ? int(threadIdx.x - 64) >> 7 : 0;   // epilogue group (== its TMEM stage when EG == 2)
-        const int te = (threadIdx.x - 64) & 127;                   // 0..127 inside the group
-        const bool dbg_lead = threadIdx.x == 64;
+        const int eg = EG == 2 ? int(threadIdx.x - Cfg::EPI0) >> 7 : 0;   // epilogue group (== its TMEM stage when EG == 2)
+        const int te = (threadIdx.x - Cfg::EPI0) & 127;                   // 0..127 inside the group
+        const bool dbg_lead = threadIdx.x == Cfg::EPI0;
         (void)dbg_lead;
         const int quarter = warp & 3;        // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;   // tile row == pixel index in the box

@@ -186,6 +186,16 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
 // shared memory with 128-bit coalesced loads, then computes from there.  Needs 16-byte
 // aligned image rows (Ws*3 % 16 == 0 and 16-byte aligned bases) - the host falls back
 // to the direct kernel otherwise.  256 threads: 128 output columns x PRE_ROWS rows.
+// u8 / 255 correctly rounded (== the reference's float32 division, dataset.py:185) without a divide or a
+// table: one Newton step on q = b * fl(1/255) is exact for all 256 inputs (checked exhaustively).
+__device__ __forceinline__ float u8_over_255(uint8_t v) {
+    const float b = (float)v;
+    const float r = 0.003921568859368563f;   // fl(1/255)
+    const float q = __fmul_rn(b, r);
+    const float rem = __fmaf_rn(-q, 255.f, b);
+    return __fmaf_rn(rem, r, q);
+}
+
 template <bool FOURTERM>
 __global__ void __launch_bounds__(256) decode_resize_smem_kernel(
     const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, const uint8_t* __restrict__ D, int B, int Hs, int Ws,
@@ -194,10 +204,6 @@ __global__ void __launch_bounds__(256) decode_resize_smem_kernel(
     int parts_per_view, int max_rows, int row_bytes) {
     SDN_PDL_ENTRY();
     extern __shared__ __align__(16) uint8_t sm[];
-    // u8 -> float / 255 as a table of the 256 correctly-rounded quotients: bit-identical to the
-    // reference's float32 division (dataset.py:185) at a fraction of the instruction count
-    __shared__ float lut[256];
-    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);
     const int n = blockIdx.y;
     const int xblocks = (W + 127) / 128;
     const int xb = blockIdx.x % xblocks;
@@ -274,10 +280,10 @@ __global__ void __launch_bounds__(256) decode_resize_smem_kernel(
                 const uint8_t* r1 = sm + (size_t)(im * max_rows + (y1 - row_first)) * row_bytes;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float a = lut[r0[c0 + c]];
-                    const float b = lut[r0[c1 + c]];
-                    const float cc = lut[r1[c0 + c]];
-                    const float e = lut[r1[c1 + c]];
+                    const float a = u8_over_255(r0[c0 + c]);
+                    const float b = u8_over_255(r0[c1 + c]);
+                    const float cc = u8_over_255(r1[c0 + c]);
+                    const float e = u8_over_255(r1[c1 + c]);
                     rgb[im][c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
                     input[((size_t)n * 6 + im * 3 + c) * plane + opix] = rgb[im][c];
                 }
