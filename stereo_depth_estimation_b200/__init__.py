@@ -3,4 +3,6 @@ sdfgeoff/stereo_depth_estimation.  Host side in Python over a C-ABI CUDA library
 (include/sdn.h -> libsdn_b200.so); see DESIGN.md and INTEGRATION.md."""
 from .model import ConvBlock, StereoUNet, load_state_dict_compat  # noqa: F401
 
-__all__ = ["StereoUNet", "ConvBlock", "load_state_dict_compat"]
+from .pipeline import SourcePrefetcher  # noqa: F401
+
+__all__ = ["StereoUNet", "ConvBlock", "load_state_dict_compat", "SourcePrefetcher"]

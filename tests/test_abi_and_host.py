@@ -163,3 +163,45 @@ def test_bench_reference_arm_contract():
                 "cpu_baseline", "e2e", "config"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_source_prefetcher_refuses_cpu_and_bad_sources():
+    """Host-side contract of the source pipeline (row N3): CUDA only, raw uint8 HWC host tensors only."""
+    from stereo_depth_estimation_b200.pipeline import SourcePrefetcher
+
+    with pytest.raises(RuntimeError):
+        SourcePrefetcher([], torch.device("cpu"))
+    good = torch.zeros(1, 4, 4, 3, dtype=torch.uint8)
+    SourcePrefetcher._check((good, good, good))
+    with pytest.raises(ValueError):
+        SourcePrefetcher._check((good, good))
+    with pytest.raises(ValueError):
+        SourcePrefetcher._check((good, good, good.float()))
+    with pytest.raises(ValueError):
+        SourcePrefetcher._check((good, good, torch.zeros(1, 4, 4, 1, dtype=torch.uint8)))
+
+
+def test_dropin_install_patches_reference_module_names():
+    """`dropin.install()` rebinds the two names the reference imports."""
+    import types
+
+    from stereo_depth_estimation_b200 import StereoUNet, dropin, load_state_dict_compat
+
+    pkg = types.ModuleType("foundation_stereo_depth")
+    mod = types.ModuleType("foundation_stereo_depth.model")
+    mod.StereoUNet = object
+    mod.load_state_dict_compat = object
+    pkg.model = mod
+    saved = {k: sys.modules.get(k) for k in ("foundation_stereo_depth", "foundation_stereo_depth.model")}
+    sys.modules["foundation_stereo_depth"] = pkg
+    sys.modules["foundation_stereo_depth.model"] = mod
+    try:
+        dropin.install()
+        assert mod.StereoUNet is StereoUNet
+        assert mod.load_state_dict_compat is load_state_dict_compat
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
