@@ -1432,10 +1432,12 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
         ++c->launches;
         aug_all = reinterpret_cast<const AugParams*>(c->aug_stage);
     }
-    // With augmentation on, samples go through in chunks whose fp32 views stay L2-resident between the
-    // decode/resize pass and the in-place augmentation pass, so DRAM sees each byte about once.
+    // SDN_PRE_CHUNK=n sends the samples through in chunks whose fp32 views stay L2-resident between the
+    // decode/resize pass and the in-place augmentation pass.  It paid while the augmentation was ALU-bound
+    // at ~1100 instructions per pixel; with the special-function-unit version the extra launches cost more
+    // than the DRAM round trip (chunk 16: 1.94 ms, whole batch: 1.51 ms at 256 pairs), so the default is off.
     static int chunk_cfg = -1;
-    if (chunk_cfg < 0) { const char* e = getenv("SDN_PRE_CHUNK"); chunk_cfg = e ? atoi(e) : 16; }
+    if (chunk_cfg < 0) { const char* e = getenv("SDN_PRE_CHUNK"); chunk_cfg = e ? atoi(e) : 0; }
     const int chunk = (aug_all != nullptr && chunk_cfg > 0) ? chunk_cfg : B;
     const size_t src_img = (size_t)Hs * Ws * 3, plane = (size_t)c->H * c->W;
     const int parts = ((c->W + 127) / 128) * ((c->H + PRE_ROWS - 1) / PRE_ROWS);
