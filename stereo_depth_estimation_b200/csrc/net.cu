@@ -640,6 +640,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
         return 0;
     }
     Tile t;
+    int plain_kpix = 64;
     if (p.halo) {
         // one image per box, TW a multiple of 8 (row shifts must be whole swizzle groups)
         double best = 1e300;
@@ -651,10 +652,13 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
             if (cost < best) { best = cost; t = Tile{TW, TH, 1}; }
         }
     } else {
-        t = choose_tile(W, H, B, 64);
+        // plain (1x1 / ConvTranspose2d / im2col'ed first layer) tiles: 128 pixels halve the per-tile handshakes
+        // (only where there are plenty of tiles: the small levels need the parallelism of 64-pixel tiles more)
+        plain_kpix = (long long)W * H * B / 128 >= 16LL * c->num_sms ? 128 : 64;
+        t = choose_tile(W, H, B, plain_kpix);
     }
     p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
-    p.kpix = 64;
+    p.kpix = p.halo ? 64 : plain_kpix;
     p.tiles_x = (W + t.TW - 1) / t.TW;
     p.tiles_y = (H + t.TH - 1) / t.TH;
     p.tiles_n = (B + t.TN - 1) / t.TN;
@@ -708,7 +712,13 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
     static int waves = -1;
     if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 2; }
-    int split = (waves * c->num_sms) / ctas_per_split;   // never spill into a partial extra wave (1 CTA per SM)
+    // ConvTranspose2d: the four quadrant variants of a pixel tile read the SAME source tile.  With one wave
+    // all four run side by side (blockIdx.z = variant, same blockIdx.x = same tiles), so the source comes from
+    // DRAM once and from L2 three times; with two waves it is streamed from DRAM twice.
+    static int convt_waves = -1;
+    if (convt_waves < 0) { const char* e = getenv("SDN_CONVT_WGRAD_WAVES"); convt_waves = e ? atoi(e) : 1; }
+    const int w_eff = p.a_variants == 4 ? convt_waves : waves;
+    int split = (w_eff * c->num_sms) / ctas_per_split;   // never spill into a partial extra wave (1 CTA per SM)
     split = std::max(1, std::min(split, ptiles));
     op.grid = dim3(split, p.unit_groups, p.m_tiles * p.a_variants);
     return 0;

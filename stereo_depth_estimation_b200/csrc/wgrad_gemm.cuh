@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
                             }
                         }
                     } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {  // kpix == 64: four K = 16 steps of two 8-row groups each
+                        // kpix / 16 K = 16 steps of two 8-row groups each (halo tiles: 64 pixels, plain tiles: 128)
+                        const int ksteps = HALO ? 4 : (p.kpix >> 4);
+#pragma unroll 4
+                        for (int k = 0; k < ksteps; ++k) {
                             const uint64_t adesc = sa + uint64_t(k * ((16 * 128) >> 4));
                             const uint64_t bk = sb + uint64_t(k * ((16 * SWB) >> 4));
                             const uint32_t acc = (it | k) != 0 ? 1u : 0u;
