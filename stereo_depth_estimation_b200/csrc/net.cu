@@ -654,7 +654,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     } else {
         // plain (1x1 / ConvTranspose2d / im2col'ed first layer) tiles: 128 pixels halve the per-tile handshakes
         // (only where there are plenty of tiles: the small levels need the parallelism of 64-pixel tiles more)
-        plain_kpix = (long long)W * H * B / 128 >= 16LL * c->num_sms ? 128 : 64;
+        plain_kpix = (long long)W * H * B / 128 >= 32LL * c->num_sms ? 128 : 64;
         t = choose_tile(W, H, B, plain_kpix);
     }
     p.TW = t.TW; p.TH = t.TH; p.TN = t.TN;
