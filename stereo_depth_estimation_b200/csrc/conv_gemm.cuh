@@ -75,7 +75,7 @@ struct alignas(64) ConvGemmParams {
 #define SDN_ABLATE(flag) false
 #endif
 
-template <int SWA, int BLOCK_N>
+template <int SWA, int BLOCK_N, int SWD_SEL = 0>
 struct CgCfg {
     static constexpr int KB = SWA / 2;  // bf16 channels per k-block
     static constexpr int A_BYTES = 128 * SWA;
@@ -83,7 +83,8 @@ struct CgCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // staging / store swizzle: 64-channel blocks, except 32-channel blocks for N = 32 and for 32-channel
     // sources (so that a 64-wide tile can be split over two 32-channel destinations: dec1 dgrad)
-    static constexpr int SWD = (BLOCK_N >= 64 && SWA == 128) ? 128 : 64;
+    // (SWD_SEL = 64 forces 32-channel blocks: a 128-wide ConvTranspose2d tile over four 32-channel quadrants)
+    static constexpr int SWD = SWD_SEL ? SWD_SEL : ((BLOCK_N >= 64 && SWA == 128) ? 128 : 64);
     static constexpr int DCH = SWD / 2;                   // channels per D block
     static constexpr int D_BLOCKS = BLOCK_N / DCH;
     static constexpr int D_BLOCK_BYTES = 128 * SWD;
@@ -134,9 +135,9 @@ struct CgCfg {
 // and step between 8-row groups by any stride.  ONE (TH+2) x (TW+2) box per (source, channel
 // block) then serves all NINE taps: tap (dy, dx) starts (dy*(TW+2) + dx) rows into the box and
 // strides (TW+2) rows between the 8-pixel image-row segments.  L2->SM rows per tile: 180 instead of 432.
-template <int SWA, int BLOCK_N, int HALO>
-__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = CgCfg<SWA, BLOCK_N>;
+template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0>
+__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL>;
     constexpr int KB = Cfg::KB;
     constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
     constexpr uint32_t SBO_A = 8 * SWA;

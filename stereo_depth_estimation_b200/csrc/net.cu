@@ -150,6 +150,7 @@ struct Act {
 struct GemmOp {
     ConvGemmParams p;
     int swa = 128, block_n = 32, grid = 1, smem = 0;
+    bool swd64 = false;  // 128-wide tile stored as four 32-channel blocks (ConvTranspose2d with Cout = 32)
     int halo = 0;  // 3x3 convs: 1 = row-halo A boxes (one per horizontal tap), 2 = one box for all nine taps; the packed weights use the matching K order
 };
 struct WgradOp {
@@ -293,6 +294,13 @@ static int launch_cg_t(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     return 0;
 }
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    if (op.swd64) {
+        if (op.swa != 128 || op.block_n != 128 || op.halo != 0) return fail("swd64 needs the plain <128,128> kernel");
+        launch_k(conv_gemm_kernel<128, 128, 0, 64>, op.grid, CgCfg<128, 128, 64>::THREADS, op.smem, st, op.p);
+        ++c->launches;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (op.halo == 2) {
         if (op.swa == 128) {
             switch (op.block_n) {
@@ -365,12 +373,13 @@ static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
 }
 static int set_smem_attrs() {
     const int big = 227 * 1024;
-#define SDN_SMEM_ATTR(...) CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
+#define SDN_SMEM_ATTR(...) CUDA_OK(cudaFuncSetAttribute((conv_gemm_kernel<__VA_ARGS__>), cudaFuncAttributeMaxDynamicSharedMemorySize, big))
     SDN_SMEM_ATTR(128, 32, 0); SDN_SMEM_ATTR(128, 64, 0); SDN_SMEM_ATTR(128, 128, 0);
     SDN_SMEM_ATTR(128, 256, 0); SDN_SMEM_ATTR(64, 32, 0); SDN_SMEM_ATTR(64, 64, 0);
     SDN_SMEM_ATTR(128, 32, 1); SDN_SMEM_ATTR(128, 64, 1); SDN_SMEM_ATTR(128, 128, 1);
     SDN_SMEM_ATTR(64, 32, 1); SDN_SMEM_ATTR(64, 64, 1);
     SDN_SMEM_ATTR(128, 32, 2); SDN_SMEM_ATTR(128, 64, 2); SDN_SMEM_ATTR(64, 32, 2); SDN_SMEM_ATTR(64, 64, 2);
+    SDN_SMEM_ATTR(128, 128, 0, 64);
 #undef SDN_SMEM_ATTR
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -461,17 +470,25 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     const int KB = op.swa / 2;
     int bn = std::min(n_per_dmap, 256);
     // narrow destinations (dgrad of a concat input): one tile spans both, so the A operand is fetched once
+    op.swd64 = false;
     if (n_per_dmap < 128 && n_total > n_per_dmap) {
         int wide = std::min(n_total, op.swa == 64 ? 64 : 128);
         const int wide_dch = (wide >= 64 && op.swa == 128) ? 64 : 32;   // store block of that tile width
         if (wide % n_per_dmap == 0 && n_per_dmap % wide_dch == 0) bn = wide;
+        else if (!conv3x3 && op.swa == 128 && wide == 128 && n_per_dmap == 32 && (flags & CG_STATS) == 0) {
+            bn = 128;            // four 32-channel quadrants from one tile: the A operand is read once, not 4x
+            op.swd64 = true;
+        }
     }
     if (op.swa == 64 && bn > 64) bn = 64;
     const int W = dviews[0].W, H = dviews[0].H;
     if (!(flags & CG_STATS)) {
         // latency regime (few pixels): narrower N tiles spread the K loop over more CTAs
         const long long m_est = ((long long)W * H * B + 127) / 128;
-        while (bn > 32 && m_est * (n_total / bn) < c->num_sms / 2) bn /= 2;
+        while (bn > 32 && m_est * (n_total / bn) < c->num_sms / 2) {
+            if (op.swd64) { op.swd64 = false; bn = std::min(n_per_dmap, 256); }   // back to one tile per quadrant
+            else bn /= 2;
+        }
     }
     if (n_per_dmap % bn != 0 && bn % n_per_dmap != 0)
         return fail("build_gemm: N %d and BLOCK_N %d do not nest", n_per_dmap, bn);
@@ -536,7 +553,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.kblocks_total = kblocks;
     if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * (op.halo == 2 ? 9 : 3), bn, op.swa));
     else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
-    const int swd = (bn >= 64 && op.swa == 128) ? 128 : 64;
+    const int swd = op.swd64 ? 64 : ((bn >= 64 && op.swa == 128) ? 128 : 64);
     const int dch = swd / 2;
     if (n_per_dmap % dch != 0) return fail("build_gemm: destination width %d not a multiple of the %d-channel store block", n_per_dmap, dch);
     for (size_t i = 0; i < dviews.size(); ++i) {
@@ -578,8 +595,13 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         stages = std::max(2, std::min(8, budget / (p.ups * unit_bytes)));
         op.smem = fixed + (res ? b_total : 0) + stages * p.ups * unit_bytes;
     } else {
-        while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
-        op.smem = cg_smem(op.swa, bn, stages);
+        if (op.swd64) {
+            while (stages > 2 && CgCfg<128, 128, 64>::smem_bytes(stages) > 220 * 1024) --stages;
+            op.smem = CgCfg<128, 128, 64>::smem_bytes(stages);
+        } else {
+            while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
+            op.smem = cg_smem(op.swa, bn, stages);
+        }
     }
     p.stages = stages;
     const int num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
