@@ -221,6 +221,12 @@ struct sdn_ctx {
     int64_t launches = 0;
     // optional per-op timing (CUDA events on the launching stream)
     bool prof = false;
+    // Backward overlap: weight gradients run on a low-priority side stream, next to the memory-bound
+    // BatchNorm backward of the following layer (dgrad -> BN backward is the critical path; a wgrad and a
+    // dgrad cannot share an SM, a wgrad and the shared-memory-free BN kernels can).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_dirty = false;
     struct ProfRec {
         const char* name;
         int layer;
@@ -1150,18 +1156,33 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
         static int wdbg_layer = -2;
         if (wdbg_layer == -2) { const char* e = getenv("SDN_DEBUG_TRACE_WGRAD"); wdbg_layer = e ? atoi(e) : -1; }
         L.wgrad.p.dbg = (i == wdbg_layer) ? c->dbg : nullptr;
-        ProfScope ps(c, st, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
-        SDN_OK(launch_wg(c, L.wgrad, st));
+        static int overlap_env = -1;
+        if (overlap_env < 0) { const char* e = getenv("SDN_WGRAD_OVERLAP"); overlap_env = e ? atoi(e) : 1; }
+        // per-op profiling times kernels with events on `st`: keep everything there while it is on
+        const bool overlap = overlap_env && c->side != nullptr && !c->prof && L.has_dgrad;
+        cudaStream_t ws = st;
+        if (overlap) {
+            CUDA_OK(cudaEventRecord(c->ev_fork, st));            // dy of this layer is ready
+            CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            ws = c->side;
+            c->side_dirty = true;
+        }
+        // the data gradient first: it heads the critical path (dgrad -> BN backward of the next layer)
+        if (overlap) SDN_OK(launch_cg(c, L.dgrad, st));
+        {
+            ProfScope ps(c, ws, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+            SDN_OK(launch_wg(c, L.wgrad, ws));
+        }
+        ProfScope ps2(c, st, L.has_dgrad ? "conv_dgrad" : "grad_unpack", i, L.has_dgrad ? 2.0 * px * L.cout * 9 * L.cin : 0.0,
+                      L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
+        if (c->grads[L.p_w] != nullptr) {
+            const int n = 9 * L.cin * L.cout;
+            launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
+                     c->accumulate);
+            ++c->launches;
+        }
+        if (L.has_dgrad && !overlap) SDN_OK(launch_cg(c, L.dgrad, st));
     }
-    ProfScope ps2(c, st, L.has_dgrad ? "conv_dgrad" : "grad_unpack", i, L.has_dgrad ? 2.0 * px * L.cout * 9 * L.cin : 0.0,
-                  L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
-    if (c->grads[L.p_w] != nullptr) {
-        const int n = 9 * L.cin * L.cout;
-        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, st, L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
-                                                               c->accumulate);
-        ++c->launches;
-    }
-    if (L.has_dgrad) SDN_OK(launch_cg(c, L.dgrad, st));
     if (L.has_dgrad && L.nsrc == 2 && c->up[(i - 10) / 2].bias_fused) {
         UpL& U = c->up[(i - 10) / 2];
         launch_k(colsum_partials_kernel, (U.cout * 32 + 255) / 256, 256, 0, st, c->stats_partials,
@@ -1305,6 +1326,13 @@ int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned 
     c->pre_only = (flags & SDN_CTX_PREPROCESS_ONLY) != 0;
     int r = plan_and_alloc(c);
     if (r != 0) { if (c->ws) cudaFree(c->ws); delete c; return r; }
+    if (!c->pre_only) {
+        int lo = 0, hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     *out = c;
     return 0;
 }
@@ -1312,6 +1340,9 @@ int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned 
 int sdn_destroy(sdn_ctx* c) {
     if (c == nullptr) return 0;
     cudaSetDevice(c->device);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ws) cudaFree(c->ws);
     delete c;
     return 0;
@@ -1441,6 +1472,11 @@ int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
             break;
         default:
             return fail("sdn_backward_stage: bad stage %d", stage);
+    }
+    if (c->side_dirty) {   // the stage's weight gradients must be complete before the caller reduces / applies them
+        CUDA_OK(cudaEventRecord(c->ev_join, c->side));
+        CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        c->side_dirty = false;
     }
     return 0;
 }
