@@ -1203,21 +1203,34 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
         launch_k(colsum_kernel, g, 256, 0, st, U.gu.p, npix, U.cout, U.bg, 0);
         ++c->launches;
     }
+    // same overlap as the 3x3 convs: the ConvTranspose2d data gradient goes first on `st`, its weight gradient
+    // (and the bias / weight unpack) run next to whatever follows on the low-priority side stream
+    static int overlap_env = -1;
+    if (overlap_env < 0) { const char* e = getenv("SDN_WGRAD_OVERLAP"); overlap_env = e ? atoi(e) : 1; }
+    const bool overlap = overlap_env && c->side != nullptr && !c->prof;
+    cudaStream_t ws = st;
+    if (overlap) {
+        CUDA_OK(cudaEventRecord(c->ev_fork, st));
+        CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        ws = c->side;
+        c->side_dirty = true;
+        SDN_OK(launch_cg(c, U.dgrad, st));
+    }
     {
-        ProfScope ps(c, st, "convT_wgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
-        SDN_OK(launch_wg(c, U.wgrad, st));
+        ProfScope ps(c, ws, "convT_wgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
+        SDN_OK(launch_wg(c, U.wgrad, ws));
     }
     ProfScope ps2(c, st, "convT_dgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
     if (c->grads[U.p_w] != nullptr) {
         const int n = 4 * U.cin * U.cout;
-        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, st, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
+        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
         ++c->launches;
     }
     if (c->grads[U.p_b] != nullptr) {
-        launch_k(copy_f32_kernel, 1, 256, 0, st, U.bg, c->grads[U.p_b], U.cout, c->accumulate);
+        launch_k(copy_f32_kernel, 1, 256, 0, ws, U.bg, c->grads[U.p_b], U.cout, c->accumulate);
         ++c->launches;
     }
-    SDN_OK(launch_cg(c, U.dgrad, st));
+    if (!overlap) SDN_OK(launch_cg(c, U.dgrad, st));
     CUDA_OK(cudaGetLastError());
     return 0;
 }
