@@ -381,6 +381,12 @@ def run_b200(args):
             roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the" \
                                      " reduce + apply kernels, averaged over the 18 layers of one step)"
             roof["algorithmic_bytes_per_launch"] = d["bytes"] / max(d["calls"], 1)
+        elif dname == "conv_fprop" and b_local == 256:
+            fam_cap = cap["families"]["forward_conv(fprop+convT_fprop)"]
+            roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["launches"]
+            roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the" \
+                                     " 22 forward conv_gemm launches of one step = 18 conv fprop + 4 ConvTranspose2d fprop)"
+            roof["algorithmic_bytes_per_launch"] = fam_cap["algorithmic_bytes"] / fam_cap["launches"]
     except Exception:
         pass
     roof["share_of_step"] = d["ms"] / total_prof_ms if total_prof_ms > 0 else None
