@@ -89,6 +89,13 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mod
         const int chan = cb * KB + c;
         v = mode == 8 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
         if (mode == 8 && oscale != nullptr) v *= oscale[row];
+    } else if (mode == 10) {
+        // first layer as a row-halo 3x1 conv over [.., 32]: dst[co][dy*32 + dx*Ci + c] = W[co][c][dy*3 + dx]
+        const int co = i / 96, k = i % 96, dy = k / 32, cc = k % 32;
+        if (cc < 3 * Ci) {
+            v = w[(co * Ci + cc % Ci) * 9 + dy * 3 + cc / Ci];
+            if (oscale != nullptr) v *= oscale[co];
+        }
     } else if (mode == 3) {
         const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
         v = w[(ci * Co + co) * 4 + q];
@@ -202,6 +209,60 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = tile[off[j] >= 0 ? off[j] + base : ZERO];
             *reinterpret_cast<uint4*>(orow + (size_t)px * 64) = pack8(f);
+        }
+    }
+}
+
+// Horizontal-taps-only variant: bf16 [B,H,W,32] with k' = dx*Cin + c (dx = 0,1,2 <-> x-1, x, x+1), zeros for
+// k' >= 3*Cin.  The first conv then runs as a row-halo 3x1 conv over this 32-channel tensor (the three
+// vertical taps are row shifts of one TMA box), which halves the bytes of the im2col'ed input: 64 instead of
+// 128 bytes per pixel written here and read back by the first layer's fprop and wgrad.
+template <int Cin>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
+                                                          int H, int W) {
+    SDN_PDL_ENTRY();
+    __shared__ float tile[Cin * IM2COL_ROWS * (IM2COL_PX + 2) + 1];
+    static_assert(3 * Cin <= 32, "first-layer channel count");
+    constexpr int PITCH = IM2COL_PX + 2;
+    constexpr int ZERO = Cin * IM2COL_ROWS * PITCH;
+    const int xblocks = (W + IM2COL_PX - 1) / IM2COL_PX;
+    const int yblocks = (H + IM2COL_ROWS - 1) / IM2COL_ROWS;
+    const int xb = blockIdx.x % xblocks;
+    const int yb = (blockIdx.x / xblocks) % yblocks;
+    const int n = blockIdx.x / (xblocks * yblocks);
+    const int x0 = xb * IM2COL_PX, y0 = yb * IM2COL_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < Cin * IM2COL_ROWS; row += 8) {
+        const int c = row / IM2COL_ROWS, r = row % IM2COL_ROWS;
+        const int yy = y0 + r;
+        const bool row_ok = yy < H;
+        const float* src = x + (((size_t)n * Cin + c) * H + (row_ok ? yy : 0)) * W;
+#pragma unroll
+        for (int t = 0; t < (PITCH + 31) / 32; ++t) {
+            const int col = lane + 32 * t;
+            const int xx = x0 + col - 1;
+            if (col < PITCH) tile[row * PITCH + col] = (row_ok && xx >= 0 && xx < W) ? __ldg(src + xx) : 0.f;
+        }
+    }
+    if (threadIdx.x == 0) tile[ZERO] = 0.f;
+    __syncthreads();
+    const int g = threadIdx.x & 3;   // 16-byte chunk (8 consecutive k') of the pixel's 64 bytes
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = g * 8 + j;
+        off[j] = k < 3 * Cin ? ((k % Cin) * IM2COL_ROWS) * PITCH + k / Cin : -1;
+    }
+    const int npx = min(IM2COL_PX, W - x0);
+    const int nrows = min(IM2COL_ROWS, H - y0);
+    for (int ry = 0; ry < nrows; ++ry) {
+        bf16* orow = out + (((size_t)n * H + y0 + ry) * W + x0) * 32 + g * 8;
+        for (int px = threadIdx.x >> 2; px < npx; px += 64) {
+            const int base = ry * PITCH + px;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = tile[off[j] >= 0 ? off[j] + base : ZERO];
+            *reinterpret_cast<uint4*>(orow + (size_t)px * 32) = pack8(f);
         }
     }
 }
@@ -743,6 +804,7 @@ __global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ 
 // mode 0: conv3x3   ws[(tap*Ci + ci)][Co]  -> grad[Co][Ci][3][3]
 // mode 2: first     ws[k][Co], k=tap*Ci+ci -> grad[Co][Ci][3][3]   (same formula, ws has >= 9*Ci rows)
 // mode 3: convT     ws[q][ci][Co]          -> grad[Ci][Co][2][2]
+// mode 4: first layer in the row-halo form (see im2col_rows_kernel)
 __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int mode, int Co, int Ci,
                                    int accumulate) {
     SDN_PDL_ENTRY();
@@ -752,6 +814,10 @@ __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restri
         if (mode == 3) {
             const int ci = i / (Co * 4), rem = i % (Co * 4), co = rem / 4, q = rem % 4;
             v = ws[((size_t)q * Ci + ci) * Co + co];
+        } else if (mode == 4) {
+            // first layer, row-halo form: ws[((dy*3 + 1)*32 + dx*Ci + c)][Co] -> grad[Co][Ci][3][3]
+            const int co = i / (Ci * 9), rem = i % (Ci * 9), ci = rem / 9, tap = rem % 9;
+            v = ws[((size_t)((tap / 3) * 3 + 1) * 32 + (tap % 3) * Ci + ci) * Co + co];
         } else {
             const int co = i / (Ci * 9), rem = i % (Ci * 9), ci = rem / 9, tap = rem % 9;
             v = ws[((size_t)tap * Ci + ci) * Co + co];

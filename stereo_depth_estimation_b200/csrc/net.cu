@@ -156,6 +156,7 @@ struct GemmOp {
 struct WgradOp {
     WgradParams p;
     int tr2_natoms = 0;   // > 0: wgrad_tr_kernel<CA, Cout, natoms> (3x3, Cout <= 64)
+    int tr2_ndx = 3;      // 1: vertical taps only (first layer, row-halo form)
     int swb = 128, smem = 0;
     dim3 grid;
 };
@@ -354,7 +355,10 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
 static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
     if (op.tr2_natoms > 0) {
         const int ca = op.swb / 2;
-        if (ca == 32 && op.p.cout == 32 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<32, 32, 1>, op.grid, 192, op.smem, st, op.p);
+        if (op.tr2_ndx == 1) {
+            if (!(ca == 32 && op.p.cout == 32 && op.tr2_natoms == 1)) return fail("vertical-only wgrad_tr needs CA 32, Cout 32, one atom");
+            launch_k(wgrad_tr_kernel<32, 32, 1, 1>, op.grid, 192, op.smem, st, op.p);
+        } else if (ca == 32 && op.p.cout == 32 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<32, 32, 1>, op.grid, 192, op.smem, st, op.p);
         else if (ca == 32 && op.p.cout == 32 && op.tr2_natoms == 2) launch_k(wgrad_tr_kernel<32, 32, 2>, op.grid, 192, op.smem, st, op.p);
         else if (ca == 32 && op.p.cout == 64 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<32, 64, 1>, op.grid, 192, op.smem, st, op.p);
         else if (ca == 64 && op.p.cout == 64 && op.tr2_natoms == 1) launch_k(wgrad_tr_kernel<64, 64, 1>, op.grid, 192, op.smem, st, op.p);
@@ -394,6 +398,7 @@ static int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<128, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_gemm_kernel<64, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 32, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 32, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 32, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<64, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -453,12 +458,19 @@ static SrcView quad_view(const Act& u, int q) {
 struct SegSpec {
     int view, dx, dy;
 };
+// SDN_FIRST_ROWS (default 1): the first conv runs as a row-halo 3x1 conv over a 32-channel tensor holding the
+// three horizontal taps (im2col_rows_kernel) instead of a K = 64 GEMM over a full 64-channel im2col
+static int first_rows() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SDN_FIRST_ROWS"); v = e ? atoi(e) : 1; }
+    return v;
+}
 static int g_halo_max_n = -1;  // SDN_HALO_MAXN: largest BLOCK_N that uses the row-halo kernel (0 disables)
 
 static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
                       const std::vector<SegSpec>& segs_in, const bf16* bmat, int n_total,
                       const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
-                      float* stats_partials, bool conv3x3 = false) {
+                      float* stats_partials, bool conv3x3 = false, int dx_taps = 3) {
     if (g_halo_max_n < 0) {
         const char* e = getenv("SDN_HALO_MAXN");
         g_halo_max_n = e ? atoi(e) : 128;
@@ -509,7 +521,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // packed weight matrix resident in shared memory and 8-pixel-wide tiles
         int cin_tot = 0;
         for (const SrcView& v : aviews) cin_tot += v.C;
-        if (op.halo && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max) op.halo = 2;
+        if (op.halo && dx_taps == 3 && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max) op.halo = 2;
     }
     if (op.halo == 2) {
         t = Tile{8, 16, 1};
@@ -529,7 +541,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         }
         // units: (horizontal tap, source); each contributes all of its channel blocks, 3 vertical taps each
         segs.clear();
-        for (int dx = -1; dx <= 1; ++dx)
+        for (int dx = (dx_taps == 3 ? -1 : 0); dx <= (dx_taps == 3 ? 1 : 0); ++dx)
             for (int sv = 0; sv < (int)aviews.size(); ++sv) segs.push_back({sv, dx, 0});
     }
     ConvGemmParams& p = op.p;
@@ -618,7 +630,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
 // Weight-gradient op.  avariants: dY views (1, or the 4 quadrants for convT);
 // bsrc: 1 or 2 X sources; taps 9 (row-halo units, see wgrad_gemm.cuh) or 1.
 static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView>& avariants, int cout,
-                       const std::vector<SrcView>& bsrc, int taps, float* out, int k_rows_valid) {
+                       const std::vector<SrcView>& bsrc, int taps, float* out, int k_rows_valid, int ndx = 3) {
     memset(&op.p, 0, sizeof op.p);
     WgradParams& p = op.p;
     bool all64 = true;
@@ -660,6 +672,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
         p.stages = std::max(2, std::min(8, (220 * 1024 - fixed) / stage_bytes));
         op.smem = fixed + p.stages * stage_bytes;
         op.tr2_natoms = natoms;
+        op.tr2_ndx = ndx;
         const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
         static int waves2 = -1;
         if (waves2 < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves2 = e ? atoi(e) : 2; }
@@ -797,7 +810,7 @@ static int plan_and_alloc(sdn_ctx* c) {
                     act(L.pool, L.cout, L.lvl + 1); act(L.gp, L.cout, L.lvl + 1);
                     carve(cur, L.pool.elems(B) / 8 * sizeof(unsigned short), (void**)&L.amax);
                 }
-                const int kdim = L.first ? 64 : 9 * L.cin;
+                const int kdim = L.first ? 288 : 9 * L.cin;   // first layer: up to 9 x 32 workspace rows (row-halo form)
                 carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wf);
                 carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wd);
                 float* vecs = nullptr;
@@ -830,7 +843,7 @@ static int plan_and_alloc(sdn_ctx* c) {
             for (int i = 0; i < 18; ++i) {
                 ConvL& L = c->conv[i];
                 L.wg = w;
-                w += (size_t)(L.first ? 64 : 9 * L.cin) * L.cout;
+                w += (size_t)(L.first ? 288 : 9 * L.cin) * L.cout;
             }
             for (int k = 0; k < 4; ++k) {
                 UpL& U = c->up[k];
@@ -884,6 +897,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
         std::vector<SrcView> av;
         std::vector<SegSpec> segs;
         if (L.first) {
+            c->x0.C = first_rows() ? 32 : 64;
             av.push_back(full_view(c->x0));
             segs.push_back({0, 0, 0});
         } else {
@@ -891,10 +905,11 @@ static int prepare_batch(sdn_ctx* c, int B) {
             for (int tap = 0; tap < 9; ++tap)
                 for (int s = 0; s < L.nsrc; ++s) segs.push_back({s, k3x3[tap].dx, k3x3[tap].dy});
         }
+        const bool rows_first = L.first && first_rows();
         SDN_OK(build_gemm(c, L.fprop, B, av, segs, L.wf, L.cout, {full_view(L.y)}, L.cout, nullptr, CG_STATS,
-                          c->stats_partials, !L.first));
+                          c->stats_partials, !L.first || rows_first, rows_first ? 1 : 3));
         SDN_OK(build_gemm(c, L.fprop_eval, B, av, segs, L.wf, L.cout, {full_view(L.a)}, L.cout, L.shift, CG_RELU,
-                          nullptr, !L.first));
+                          nullptr, !L.first || rows_first, rows_first ? 1 : 3));
         // ---- data gradient: conv3x3 of dy with flipped / transposed weights
         if (L.has_dgrad) {
             std::vector<SegSpec> dsegs(k3x3, k3x3 + 9);
@@ -924,8 +939,10 @@ static int prepare_batch(sdn_ctx* c, int B) {
         std::vector<SrcView> bs;
         if (L.first) bs.push_back(full_view(c->x0));
         else for (int s = 0; s < L.nsrc; ++s) bs.push_back(full_view(*L.src[s]));
-        SDN_OK(build_wgrad(c, L.wgrad, B, {full_view(L.dy)}, L.cout, bs, L.first ? 1 : 9, L.wg,
-                           L.first ? 64 : 9 * L.cin));
+        if (rows_first) SDN_OK(build_wgrad(c, L.wgrad, B, {full_view(L.dy)}, L.cout, bs, 9, L.wg, 288, 1));
+        else SDN_OK(build_wgrad(c, L.wgrad, B, {full_view(L.dy)}, L.cout, bs, L.first ? 1 : 9, L.wg, L.first ? 64 : 9 * L.cin));
+        if (rows_first && L.wgrad.tr2_natoms == 0) return fail("first layer: the row-halo form needs the wgrad_tr kernel");
+        if (rows_first && (L.fprop.halo != 1 || L.fprop_eval.halo != 1)) return fail("first layer: the row-halo form needs the row-halo conv kernel");
     }
     for (int k = 0; k < 4; ++k) {
         UpL& U = c->up[k];
@@ -987,7 +1004,9 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
         const float* w = c->params[L.p_w];
-        if (L.first) {
+        if (L.first && first_rows()) {
+            add(w, L.wf, fold ? L.scale : nullptr, 10, L.cout, L.cin, 32, L.cout * 96);
+        } else if (L.first) {
             add(w, L.wf, fold ? L.scale : nullptr, 2, L.cout, L.cin, 64, L.cout * 64);
         } else {
             const int n = 9 * L.cin * L.cout;
@@ -1045,9 +1064,13 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     const int H = c->H, W = c->W;
     {
         const double px = (double)B * H * W;
-        ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + 64 * 2));
-        launch_k(im2col_first_kernel<6>, B * ((H + IM2COL_ROWS - 1) / IM2COL_ROWS) * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st, 
-            x, c->x0.p, B, H, W);
+        ProfScope ps(c, st, "im2col_first", 0, 0.0, px * (6 * 4 + c->x0.C * 2));
+        if (first_rows())
+            launch_k(im2col_rows_kernel<6>, B * ((H + IM2COL_ROWS - 1) / IM2COL_ROWS) * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st,
+                     x, c->x0.p, B, H, W);
+        else
+            launch_k(im2col_first_kernel<6>, B * ((H + IM2COL_ROWS - 1) / IM2COL_ROWS) * ((W + IM2COL_PX - 1) / IM2COL_PX), 256, 0, st,
+                     x, c->x0.p, B, H, W);
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
@@ -1064,7 +1087,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             const double px = (double)B * L.y.H * L.y.W;
             {
                 ProfScope ps(c, st, "conv_fprop_eval", i, 2.0 * px * L.cout * 9 * L.cin,
-                             px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+                             px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
                 SDN_OK(launch_cg(c, L.fprop_eval, st));
             }
             if (L.pooled_out) {
@@ -1087,7 +1110,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
         }
         {
             const double px = (double)B * L.y.H * L.y.W;
-            ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+            ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
             SDN_OK(launch_cg(c, op, st));
         }
         ProfScope ps(c, st, "bn_relu_pool", i, 0.0,
@@ -1170,14 +1193,14 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
         // the data gradient first: it heads the critical path (dgrad -> BN backward of the next layer)
         if (overlap) SDN_OK(launch_cg(c, L.dgrad, st));
         {
-            ProfScope ps(c, ws, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? 64 : L.cin) + L.cout) * 2);
+            ProfScope ps(c, ws, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
             SDN_OK(launch_wg(c, L.wgrad, ws));
         }
         ProfScope ps2(c, st, L.has_dgrad ? "conv_dgrad" : "grad_unpack", i, L.has_dgrad ? 2.0 * px * L.cout * 9 * L.cin : 0.0,
                       L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
         if (c->grads[L.p_w] != nullptr) {
             const int n = 9 * L.cin * L.cout;
-            launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, L.wg, c->grads[L.p_w], L.first ? 2 : 0, L.cout, L.cin,
+            launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, L.wg, c->grads[L.p_w], L.first ? (first_rows() ? 4 : 2) : 0, L.cout, L.cin,
                      c->accumulate);
             ++c->launches;
         }

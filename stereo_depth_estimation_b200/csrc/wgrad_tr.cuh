@@ -22,7 +22,7 @@
 
 namespace sdn {
 
-template <int CA, int COUT, int NATOMS>
+template <int CA, int COUT, int NATOMS, int NDX = 3>
 struct WtrCfg {
     static constexpr int SWB = CA * 2;                       // X swizzle row
     static constexpr int SWY = COUT * 2;                     // dY swizzle row
@@ -33,15 +33,16 @@ struct WtrCfg {
     static constexpr int X_TX = BOX_W * BOX_H * SWB;         // bytes one X box actually delivers
     static constexpr int STAGE_BYTES = Y_BYTES + NATOMS * X_BYTES;
     static constexpr int COLS_PER_UNIT = COUT * (CA == 64 ? 2 : 1);
-    static constexpr int COLS = NATOMS * 3 * COLS_PER_UNIT;
+    static constexpr int COLS = NATOMS * NDX * COLS_PER_UNIT;
     static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
     static_assert(COLS <= 512, "accumulators exceed TMEM");
     static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 4 * 32 * 33 * 4 + 256; }
 };
 
-template <int CA, int COUT, int NATOMS>
+// NDX = 1: vertical taps only (the first layer in its row-halo form): the single horizontal position is the centre.
+template <int CA, int COUT, int NATOMS, int NDX = 3>
 __global__ void __launch_bounds__(192, 1) wgrad_tr_kernel(const __grid_constant__ WgradParams p) {
-    using Cfg = WtrCfg<CA, COUT, NATOMS>;
+    using Cfg = WtrCfg<CA, COUT, NATOMS, NDX>;
     constexpr int SWB = Cfg::SWB, SWY = Cfg::SWY;
     constexpr uint32_t LAYOUT_X = (SWB == 128) ? 2u : 4u;
     constexpr uint32_t LAYOUT_Y = (SWY == 128) ? 2u : 4u;
@@ -141,10 +142,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tr_kernel(const __grid_constant_
 #pragma unroll
                 for (int a = 0; a < NATOMS; ++a) {
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
+                    for (int dxl = 0; dxl < NDX; ++dxl) {
+                        constexpr int DX0 = NDX == 1 ? 1 : 0;
+                        const int dx = dxl + DX0;
                         const uint64_t ydesc = ys + uint64_t((k * 16 * SWY) >> 4);
                         const uint64_t xdesc = xs + uint64_t((a * Cfg::X_BYTES + (2 * k) * ROW10 + dx * SWB) >> 4);
-                        const uint32_t d = tmem_base + uint32_t((a * 3 + dx) * Cfg::COLS_PER_UNIT);
+                        const uint32_t d = tmem_base + uint32_t((a * NDX + dxl) * Cfg::COLS_PER_UNIT);
                         ptx::tc_mma_bf16_pred(d, xdesc, ydesc, IDESC128, acc, lead);
                         if (CA == 64)
                             ptx::tc_mma_bf16_pred(d + COUT, xdesc + uint64_t((2 * ROW10) >> 4), ydesc, IDESC64, acc, lead);
@@ -167,8 +170,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tr_kernel(const __grid_constant_
         // transpose each warp's 32 rows x 32 columns through shared memory so that one red instruction
         // covers 32 CONSECUTIVE output channels of one workspace row
         float* tsm = tsm_base + (warp - 2) * (32 * 33);
-        for (int g = 0; g < NATOMS * 3; ++g) {
-            const int ca = atom0 + g / 3, dxi = g % 3;
+        for (int g = 0; g < NATOMS * NDX; ++g) {
+            const int ca = atom0 + g / NDX, dxi = NDX == 1 ? 1 : g % NDX;
             if (ca >= p.atoms_per_tap) break;
             for (int h = 0; h < HALVES; ++h) {
                 for (int ch = 0; ch < COUT / 32; ++ch) {
