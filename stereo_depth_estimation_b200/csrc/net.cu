@@ -521,7 +521,12 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // packed weight matrix resident in shared memory and 8-pixel-wide tiles
         int cin_tot = 0;
         for (const SrcView& v : aviews) cin_tot += v.C;
-        if (op.halo && dx_taps == 3 && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max) op.halo = 2;
+        // (two pipeline stages of one 18x10 box must still fit next to the weights and the store staging)
+        const int box9_stage = (10 * 18 * op.swa + 1023) & ~1023;
+        const int box9_need = (bn <= 64 ? cg_smem_halo(op.swa, bn, 0, box9_stage) : 1 << 30) + 9 * cin_tot * bn * 2 + 2 * box9_stage;
+        if (op.halo && dx_taps == 3 && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max &&
+            box9_need <= 227 * 1024)
+            op.halo = 2;
     }
     if (op.halo == 2) {
         t = Tile{8, 16, 1};
