@@ -331,19 +331,26 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
                                     unsigned short* __restrict__ amax, int B, int H, int W, int C) {
     SDN_PDL_ENTRY();
     const int CG = C >> 3;
+    // the grid stride (gridDim.x * 256) is a multiple of CG (<= 64), so a thread keeps ONE channel group: its
+    // scale / shift live in registers.  Re-loading them per item cost 16 scalar loads (8 cache lines each for
+    // wide layers) per 16 bytes of payload and made the 128..512-channel layers LSU-bound.
+    const int cg = int(((long long)blockIdx.x * blockDim.x + threadIdx.x) % CG);
+    float sc[8], sh[8];
+    {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8) + 1);
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8) + 1);
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+    }
     if (POOL) {
         const int H2 = H >> 1, W2 = W >> 1;
         const long long total = (long long)B * H2 * W2 * CG;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
              i += (long long)gridDim.x * blockDim.x) {
-            const int cg = int(i % CG);
             const long long qd = i / CG;
             const int x2 = int(qd % W2);
             const int y2 = int((qd / W2) % H2);
             const int n = int(qd / ((long long)W2 * H2));
-            float sc[8], sh[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cg * 8 + j); sh[j] = __ldg(shift + cg * 8 + j); }
             float mx[8];
             unsigned am = 0;   // 2 bits per channel: quad position of the FIRST maximum (nn.MaxPool2d routing)
 #pragma unroll
@@ -373,12 +380,10 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
         const long long total = (long long)B * H * W * CG;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
              i += (long long)gridDim.x * blockDim.x) {
-            const int cg = int(i % CG);
             float f[8];
             unpack8(ldg16(y + i * 8), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                f[j] = fmaxf(fmaf(f[j], __ldg(scale + cg * 8 + j), __ldg(shift + cg * 8 + j)), 0.f);
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
             *reinterpret_cast<uint4*>(a + i * 8) = pack8(f);
         }
     }
