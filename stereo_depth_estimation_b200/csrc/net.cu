@@ -275,8 +275,8 @@ static inline int lvl_w(const sdn_ctx* c, int lvl) { return c->W >> (lvl - 1); }
 // `griddepcontrol.launch_dependents` at entry and blocks on `griddepcontrol.wait` before it touches
 // memory, so the NEXT kernel's launch and prologue (barrier init, TMEM allocation, descriptor prefetch)
 // overlap the tail of the previous one.  SDN_PDL=0 / 1 forces it off / on.
-// measured: +1.3 % at 32 pairs per GPU, -4 % at 256 (parked dependents take SM resources from long
-// memory-bound kernels), so the default follows the batch (set in prepare_batch)
+// measured: +1.3 % at 32 pairs per GPU, neutral at 64, -1 % at 128, -4 % at 256 (parked dependents take SM
+// resources from long memory-bound kernels), so the default follows the batch
 static int g_pdl_auto = 0;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -1054,7 +1054,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     if (c->pre_only) return fail("sdn_forward: context was created with SDN_CTX_PREPROCESS_ONLY");
     if (!c->have_params) return fail("sdn_forward: call sdn_set_params first");
     SDN_OK(prepare_batch(c, B));
-    g_pdl_auto = (long long)B * c->H * c->W <= 64LL * 240 * 320 ? 1 : 0;
+    g_pdl_auto = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
     if (!training && dirty) {
         // eval: scale/shift from the running statistics, folded into the weights at pack time
         for (int i = 0; i < 18; ++i) {
@@ -1532,7 +1532,7 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     if (Hs < 1 || Ws < 1) return fail("sdn_preprocess: bad source size %dx%d", Hs, Ws);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaSetDevice(c->device));
-    g_pdl_auto = (long long)B * c->H * c->W <= 64LL * 240 * 320 ? 1 : 0;
+    g_pdl_auto = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
     if (valid_count != nullptr) SDN_OK(zero_fill(c, valid_count, sizeof(unsigned long long), st));
     const AugParams* aug_all = reinterpret_cast<const AugParams*>(aug_dev);
     if (aug_all != nullptr && (flags & SDN_PREPROCESS_AUG_HOST)) {
