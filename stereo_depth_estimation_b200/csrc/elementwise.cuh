@@ -54,15 +54,18 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 // mode 8: conv3x3 forward   dst[co][k] = W[co][channel][tap];  mode 9: dgrad  dst[ci][k] = W[channel][ci][8 - tap]
 // oscale (modes 0, 2, 5, 8 only): per-output-channel factor folded into the packed weights
 // (eval-mode BatchNorm: w' = w * gamma / sqrt(running_var + eps)); nullptr = 1.
+// Channel counts of every 3x3 / 2x2 layer are powers of two (32..512): the index decoding uses shifts and
+// masks (plus divisions by the constants 3 and 9); runtime integer divisions made this kernel ALU-bound.
 __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mode, int Co, int Ci, int Kpad,
                                             const float* __restrict__ oscale, int i) {
     float v = 0.f;
+    const int lCi = 31 - __clz(Ci), lCo = 31 - __clz(Co);
     if (mode == 0) {
-        const int co = i / (9 * Ci), rem = i % (9 * Ci), tap = rem / Ci, ci = rem % Ci;
+        const int q = i >> lCi, co = q / 9, tap = q - 9 * co, ci = i & (Ci - 1);
         v = w[(co * Ci + ci) * 9 + tap];
         if (oscale != nullptr) v *= oscale[co];
     } else if (mode == 1) {
-        const int ci = i / (9 * Co), rem = i % (9 * Co), tap = rem / Co, co = rem % Co;
+        const int q = i >> lCo, ci = q / 9, tap = q - 9 * ci, co = i & (Co - 1);
         v = w[(co * Ci + ci) * 9 + (8 - tap)];
     } else if (mode == 2) {
         const int co = i / Kpad, k = i % Kpad;
@@ -71,24 +74,24 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mod
             v = w[(co * Ci + ci) * 9 + tap];
             if (oscale != nullptr) v *= oscale[co];
         }
-    } else if (mode == 5 || mode == 6) {
-        const int KB = Kpad;
-        const int kin = mode == 5 ? Ci : Co;      // channels on the K side
-        const int row = i / (9 * kin), k = i % (9 * kin);
-        const int blocks = kin / KB;
-        const int c = k % KB, dy = (k / KB) % 3, unit = k / (3 * KB);
-        const int dx = unit / blocks, cb = unit % blocks;
-        const int chan = cb * KB + c, tap = dy * 3 + dx;
-        v = mode == 5 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
-        if (mode == 5 && oscale != nullptr) v *= oscale[row];
-    } else if (mode == 8 || mode == 9) {
-        const int KB = Kpad;
-        const int kin = mode == 8 ? Ci : Co;
-        const int row = i / (9 * kin), k = i % (9 * kin);
-        const int c = k % KB, tap = (k / KB) % 9, cb = k / (9 * KB);
-        const int chan = cb * KB + c;
-        v = mode == 8 ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
-        if (mode == 8 && oscale != nullptr) v *= oscale[row];
+    } else if (mode == 5 || mode == 6 || mode == 8 || mode == 9) {
+        const int KB = Kpad, lKB = 31 - __clz(KB);
+        const bool fwd = mode == 5 || mode == 8;
+        const int lk = fwd ? lCi : lCo;             // channels on the K side (a power of two)
+        const int q = i >> lk, row = q / 9;
+        const int k = i - ((row * 9) << lk);
+        const int c = k & (KB - 1), u = k >> lKB;
+        int chan, tap;
+        if (mode <= 6) {   // row-halo order: u = (dx*blocks + cb)*3 + dy
+            const int dy = u % 3, unit = u / 3, lb = lk - lKB;
+            const int dx = unit >> lb, cb = unit & ((1 << lb) - 1);
+            chan = (cb << lKB) + c; tap = dy * 3 + dx;
+        } else {           // box9 order: u = cb*9 + tap
+            const int cb = u / 9;
+            tap = u - 9 * cb; chan = (cb << lKB) + c;
+        }
+        v = fwd ? w[(row * Ci + chan) * 9 + tap] : w[(chan * Ci + row) * 9 + (8 - tap)];
+        if (fwd && oscale != nullptr) v *= oscale[row];
     } else if (mode == 10) {
         // first layer as a row-halo 3x1 conv over [.., 32]: dst[co][dy*32 + dx*Ci + c] = W[co][c][dy*3 + dx]
         const int co = i / 96, k = i % 96, dy = k / 32, cc = k % 32;
@@ -97,13 +100,13 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mod
             if (oscale != nullptr) v *= oscale[co];
         }
     } else if (mode == 3) {
-        const int row = i / Ci, ci = i % Ci, q = row / Co, co = row % Co;
+        const int ci = i & (Ci - 1), row = i >> lCi, q = row >> lCo, co = row & (Co - 1);
         v = w[(ci * Co + co) * 4 + q];
     } else if (mode == 4) {
-        const int ci = i / (4 * Co), rem = i % (4 * Co), q = rem / Co, co = rem % Co;
+        const int co = i & (Co - 1), t = i >> lCo, q = t & 3, ci = t >> 2;
         v = w[(ci * Co + co) * 4 + q];
     } else {  // mode 7: bias replicated over the 4 convT quadrants (fp32 destination)
-        v = w[i % Co];
+        v = w[i & (Co - 1)];
     }
     return v;
 }
