@@ -659,13 +659,35 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
 #pragma unroll
         for (int j = 0; j < 72; ++j) acc[j] = 0.f;
     }
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
-         p += (long long)gridDim.x * blockDim.x) {
+    // One block per SM fits (the 66 weight-gradient accumulators live in registers): two warps per scheduler
+    // cannot hide a ~1 us DRAM round trip per pixel, so the NEXT pixel's operands (64 bytes of d1, target, mask)
+    // are requested before the current one is processed.
+    const long long p_first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p_step = (long long)gridDim.x * blockDim.x;
+    uint4 nxt[4];
+    float nxt_tg = 0.f;
+    uint8_t nxt_mk = 0;
+    if (p_first < npix) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) nxt[v] = ldg16(d1 + p_first * 32 + v * 8);
+        if (MODE == 2) { nxt_tg = __ldg(target + p_first); nxt_mk = __ldg(mask + p_first); }
+    }
+    for (long long p = p_first; p < npix; p += p_step) {
         float f[32];
+        uint4 cur[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cur[v] = nxt[v];
+        const float cur_tg = nxt_tg;
+        const uint8_t cur_mk = nxt_mk;
+        if (p + p_step < npix) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) nxt[v] = ldg16(d1 + (p + p_step) * 32 + v * 8);
+            if (MODE == 2) { nxt_tg = __ldg(target + p + p_step); nxt_mk = __ldg(mask + p + p_step); }
+        }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             float t8[8];
-            unpack8(ldg16(d1 + p * 32 + v * 8), t8);
+            unpack8(cur[v], t8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[v * 8 + j] = t8[j];
         }
@@ -684,8 +706,8 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
             gd = g_disp[p];
             gl = g_logvar != nullptr ? g_logvar[p] : 0.f;
         } else {
-            const float tg = target[p];
-            const bool m = (mask[p] != 0) && isfinite(tg);
+            const float tg = cur_tg;
+            const bool m = (cur_mk != 0) && isfinite(tg);
             gd = 0.f; gl = 0.f;
             if (m) {
                 const float diff = dsp - tg;
