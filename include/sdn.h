@@ -75,7 +75,11 @@ int sdn_forward(sdn_ctx* ctx, const float* x, float* disp, float* logvar, int B,
  * dL/d(disp), dL/d(logvar) (fp32 [B,1,H,W], g_logvar may be NULL) and runs the
  * head backward.  Then sdn_backward_stage(s) for s = 0..SDN_NUM_STAGES-1 in
  * order; when stage s has run, the gradients of the parameters in
- * sdn_stage_param_range(s) are final in the caller's grad tensors. */
+ * sdn_stage_param_range(s) are final in the caller's grad tensors.
+ * Stream semantics: all work is ordered on `stream`.  Internally the weight gradients of a stage run
+ * on a context-owned low-priority side stream (forked after each layer's BatchNorm backward, joined
+ * back into `stream` before sdn_backward_stage returns), so whatever the caller enqueues on `stream`
+ * after the call - an all-reduce of the stage's gradient bucket, the optimizer - sees final values. */
 int sdn_backward_begin(sdn_ctx* ctx, const float* g_disp, const float* g_logvar, int accumulate, void* stream);
 int sdn_backward_stage(sdn_ctx* ctx, int stage, void* stream);
 int sdn_stage_param_range(int stage, int* first_param, int* num_params);
