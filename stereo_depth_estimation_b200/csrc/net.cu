@@ -680,7 +680,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
         op.tr2_ndx = ndx;
         const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
         static int waves2 = -1;
-        if (waves2 < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves2 = e ? atoi(e) : 2; }
+        if (waves2 < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves2 = e ? atoi(e) : 1; }
         int split = std::max(1, std::min((waves2 * c->num_sms) / p.unit_groups, ptiles));
         op.grid = dim3(split, p.unit_groups, 1);
         return 0;
@@ -757,7 +757,9 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
     static int waves = -1;
-    if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 2; }
+    // one wave measured best with the current kernels (256 pairs: +1.2 %, 32 pairs: +4.6 % over two waves:
+    // half the split-K partial sums to merge); the older kernels preferred two
+    if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 1; }
     // ConvTranspose2d: the four quadrant variants of a pixel tile read the SAME source tile.  With one wave
     // all four run side by side (blockIdx.z = variant, same blockIdx.x = same tiles), so the source comes from
     // DRAM once and from L2 three times; with two waves it is streamed from DRAM twice.
