@@ -86,17 +86,55 @@ int sdn_stage_param_range(int stage, int* first_param, int* num_params);
 
 /* Fused heteroscedastic Laplace loss (train.py:329-357) on the forward just run:
  * mask = valid_mask & isfinite(target); n = sum(mask) (device side);
- * sums[0..3] += sum nll, sum |diff|, sum diff^2, sum exp(0.5*logvar) over mask,
- * *count += n; seeds the backward with dL/dz for L = sum(nll)/n_norm where
+ * sums[0..3] (device fp64, like the reference's Python-float running sums) += sum nll, sum |diff|,
+ * sum diff^2, sum exp(0.5*logvar) over mask, *count += n; seeds the backward with dL/dz for L = sum(nll)/n_norm where
  * n_norm = *n_norm_dev (a device u64, e.g. the all-reduced global count) or n if
  * NULL.  with_backward == 0 gives the validation path (metrics only).
  * disp / logvar outputs are optional (NULL skips the store). */
 int sdn_loss_begin(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask, float* disp, float* logvar,
-                   float* sums4, unsigned long long* count, const unsigned long long* n_norm_dev, int with_backward,
+                   double* sums4, unsigned long long* count, const unsigned long long* n_norm_dev, int with_backward,
                    int accumulate, void* stream);
 /* n = sum(valid_mask & isfinite(target)) into *count_out (device u64, pre-zeroed by the callee). */
 int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask, int B, unsigned long long* count_out,
                     void* stream);
+
+/* ---- one-call steps --------------------------------------------------------------------------------
+ * sdn_train_step = the loop body of run_epoch for one assembled batch, train.py:325-342 (everything but
+ * optimizer.step(), which is sdn_adamw_step): train-mode forward -> n = sum(valid_mask & isfinite(target))
+ * (skipped with SDN_STEP_HAVE_COUNT: *n_norm already holds this rank's count, e.g. from sdn_preprocess) ->
+ * [all-reduce of n: the loss normaliser is the GLOBAL valid count] -> fused loss, metric sums and head
+ * backward (sdn_loss_begin semantics: sums4 / count accumulate) -> the four backward stages; with a
+ * communicator (sdn_comm_init) each stage's gradient bucket is all-reduced (sum) on the context's
+ * communicator stream while the next stage runs, and `stream` waits for the last bucket before the call's
+ * work ends.  Gradients go to the destinations given to sdn_set_params; for data parallelism the
+ * destinations of each stage (sdn_stage_param_range) must be consecutive views of one buffer.
+ * On return *n_norm (device) holds the global count: 0 means "skip the optimizer step" (train.py:331-332);
+ * sdn_adamw_step takes it as its gate, so no host synchronisation is needed.
+ * sdn_eval_step = run_epoch with optimizer=None (train.py:618) / log_epoch_previews (train.py:268-272):
+ * eval-mode forward (running statistics) + the same metric sums; disp / logvar are optional outputs. */
+#define SDN_STEP_HAVE_COUNT 1u
+#define SDN_STEP_NO_OVERLAP 2u /* all-reduce on `stream` itself (bit-identical result; the dp_check leg of bench.py) */
+int sdn_train_step(sdn_ctx* ctx, const float* x, const float* target, const uint8_t* valid_mask, int B,
+                   int params_dirty, double* sums4, unsigned long long* count, unsigned long long* n_norm,
+                   unsigned flags, void* stream);
+int sdn_eval_step(sdn_ctx* ctx, const float* x, const float* target, const uint8_t* valid_mask, int B,
+                  int params_dirty, float* disp, float* logvar, double* sums4, unsigned long long* count,
+                  void* stream);
+
+/* ---- data parallelism (new: the reference is single-process) -------------------------------
+ * One process per GPU, one NCCL communicator per context.  Rank 0 calls sdn_comm_unique_id and hands the
+ * 128 bytes to the other ranks by any means (torch.distributed store, MPI, a file); every rank then calls
+ * sdn_comm_init (collective).  NCCL is resolved with dlopen("libnccl.so.2") at that moment - inside a
+ * PyTorch process that is the copy torch already mapped - so single-GPU users never need it.
+ * sdn_comm_allreduce: in-place sum over ranks on `stream` (metric sums, checks); no-op for world 1. */
+#define SDN_F32 0
+#define SDN_F64 1
+#define SDN_U64 2
+int sdn_comm_unique_id(void* out128_host);
+int sdn_comm_init(sdn_ctx* ctx, const void* unique_id_128_host, int rank, int world);
+int sdn_comm_destroy(sdn_ctx* ctx);
+int sdn_comm_world(const sdn_ctx* ctx);
+int sdn_comm_allreduce(sdn_ctx* ctx, void* buf, int64_t count, int dtype, void* stream);
 
 /* FoundationStereoDataset.__getitem__ + default collate (dataset.py:184-212,
  * 248-270, 302-311) for a batch of raw uint8 HWC images already on the device:

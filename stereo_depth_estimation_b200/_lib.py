@@ -20,6 +20,9 @@ NUM_STAGES = 4
 RESIZE_FOURTERM = 1
 PREPROCESS_AUG_HOST = 4
 CTX_PREPROCESS_ONLY = 1
+STEP_HAVE_COUNT = 1
+STEP_NO_OVERLAP = 2
+F32, F64, U64 = 0, 1, 2
 
 # every symbol include/sdn.h declares (tests check that the .so exports them all)
 EXPORTS = (
@@ -35,6 +38,13 @@ EXPORTS = (
     "sdn_stage_param_range",
     "sdn_loss_begin",
     "sdn_count_valid",
+    "sdn_train_step",
+    "sdn_eval_step",
+    "sdn_comm_unique_id",
+    "sdn_comm_init",
+    "sdn_comm_destroy",
+    "sdn_comm_world",
+    "sdn_comm_allreduce",
     "sdn_preprocess",
     "sdn_debug_read",
     "sdn_adamw_step",
@@ -100,6 +110,22 @@ def load() -> ctypes.CDLL:
                                    c_int, c_int, c_void_p]
     lib.sdn_count_valid.restype = c_int
     lib.sdn_count_valid.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.sdn_train_step.restype = c_int
+    lib.sdn_train_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_uint, c_void_p]
+    lib.sdn_eval_step.restype = c_int
+    lib.sdn_eval_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]
+    lib.sdn_comm_unique_id.restype = c_int
+    lib.sdn_comm_unique_id.argtypes = [c_void_p]
+    lib.sdn_comm_init.restype = c_int
+    lib.sdn_comm_init.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    lib.sdn_comm_destroy.restype = c_int
+    lib.sdn_comm_destroy.argtypes = [c_void_p]
+    lib.sdn_comm_world.restype = c_int
+    lib.sdn_comm_world.argtypes = [c_void_p]
+    lib.sdn_comm_allreduce.restype = c_int
+    lib.sdn_comm_allreduce.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint, c_void_p]

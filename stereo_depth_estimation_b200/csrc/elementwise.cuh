@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 //         nn.Module drop-in path: the loss lives in train.py:329-340).
 // MODE 2: fused heteroscedastic Laplace loss (train.py:329-357): forward,
 //         5 metric sums, and the loss gradient seeded with 1/n, n read from device.
-// sums layout (fp32, atomically accumulated, pre-zeroed by the caller):
+// sums layout (fp64, atomically accumulated across blocks and across steps, pre-zeroed by the caller: the
+// reference accumulates its running sums in Python doubles, train.py:345-357):
 //   [0] sum nll  [1] sum |diff|  [2] sum diff^2  [3] sum exp(0.5*logvar); the valid count is a separate u64
 // head_grads layout: [0,32) dW_d  [32] db_d  [33,65) dW_l  [65] db_l
 template <int MODE>
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
                                                    const float* __restrict__ target,
                                                    const uint8_t* __restrict__ mask,
                                                    const unsigned long long* __restrict__ n_valid,
-                                                   float* __restrict__ sums,
+                                                   double* __restrict__ sums,
                                                    unsigned long long* __restrict__ count_out,
                                                    bf16* __restrict__ g_d1, float* __restrict__ head_grads,
                                                    long long npix) {
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
         for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
         if (threadIdx.x < 66) atomicAdd(head_grads + threadIdx.x, v);
         else if (MODE == 2) {
-            if (threadIdx.x < 70) atomicAdd(sums + (threadIdx.x - 66), v);
+            if (threadIdx.x < 70) atomicAdd(sums + (threadIdx.x - 66), (double)v);
             else atomicAdd(count_out, (unsigned long long)v);  // block partial < 2^24: exact
         }
     }

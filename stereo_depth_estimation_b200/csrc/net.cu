@@ -9,6 +9,8 @@
 //   enc1..enc4, bottleneck, (up4,dec4) .. (up1,dec1), disparity/logvar heads.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is resolved at run time (sdn_comm_init), never linked
 
 #include <algorithm>
 #include <cmath>
@@ -50,6 +52,12 @@ static int fail(const char* fmt, ...) {
     do {                          \
         int r_ = (call);          \
         if (r_ != 0) return r_;   \
+    } while (0)
+// every C-ABI entry: select the context's device and its launch mode for this host thread
+#define SDN_ENTER(c)                            \
+    do {                                        \
+        CUDA_OK(cudaSetDevice((c)->device));    \
+        t_pdl = (c)->pdl;                       \
     } while (0)
 
 // ------------------------------------------------------- tensor-map encode
@@ -219,6 +227,7 @@ struct sdn_ctx {
     bool pre_only = false;  // SDN_CTX_PREPROCESS_ONLY: no network workspace
     long long* dbg = nullptr;  // timing forensics buffer (3 roles x 16 tiles x 8 events)
     int accumulate = 0;
+    int pdl = 0;   // programmatic dependent launch for this context's kernels (small per-GPU batches only)
     int64_t launches = 0;
     // optional per-op timing (CUDA events on the launching stream)
     bool prof = false;
@@ -228,6 +237,12 @@ struct sdn_ctx {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_dirty = false;
+    // Data parallelism (sdn_comm_init): one NCCL communicator per context; gradient buckets are all-reduced on
+    // `comm_stream`, forked from the caller's stream after each backward stage and joined at the end of the step.
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
     struct ProfRec {
         const char* name;
         int layer;
@@ -277,12 +292,17 @@ static inline int lvl_w(const sdn_ctx* c, int lvl) { return c->W >> (lvl - 1); }
 // overlap the tail of the previous one.  SDN_PDL=0 / 1 forces it off / on.
 // measured: +1.3 % at 32 pairs per GPU, neutral at 64, -1 % at 128, -4 % at 256 (parked dependents take SM
 // resources from long memory-bound kernels), so the default follows the batch
-static int g_pdl_auto = 0;
+// The switch belongs to the CONTEXT (sdn_ctx::pdl, chosen from its batch); every C-ABI entry copies it into this
+// thread-local before it launches anything, so two contexts / two host threads never see each other's choice.
+static thread_local int t_pdl = 0;
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    static int pdl_env = -2;
-    if (pdl_env == -2) { const char* e = getenv("SDN_PDL"); pdl_env = e ? atoi(e) : -1; }
-    const int pdl = pdl_env >= 0 ? pdl_env : g_pdl_auto;
+    static const int pdl_env = env_int("SDN_PDL", -1);
+    const int pdl = pdl_env >= 0 ? pdl_env : t_pdl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -403,6 +423,8 @@ static int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<32, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<64, 64, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute((wgrad_tr_kernel<64, 32, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
 }
 
@@ -461,20 +483,15 @@ struct SegSpec {
 // SDN_FIRST_ROWS (default 1): the first conv runs as a row-halo 3x1 conv over a 32-channel tensor holding the
 // three horizontal taps (im2col_rows_kernel) instead of a K = 64 GEMM over a full 64-channel im2col
 static int first_rows() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SDN_FIRST_ROWS"); v = e ? atoi(e) : 1; }
+    static const int v = env_int("SDN_FIRST_ROWS", 1);
     return v;
 }
-static int g_halo_max_n = -1;  // SDN_HALO_MAXN: largest BLOCK_N that uses the row-halo kernel (0 disables)
 
 static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
                       const std::vector<SegSpec>& segs_in, const bf16* bmat, int n_total,
                       const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
                       float* stats_partials, bool conv3x3 = false, int dx_taps = 3) {
-    if (g_halo_max_n < 0) {
-        const char* e = getenv("SDN_HALO_MAXN");
-        g_halo_max_n = e ? atoi(e) : 128;
-    }
+    static const int g_halo_max_n = env_int("SDN_HALO_MAXN", 128);   // largest BLOCK_N that uses the row-halo kernel (0 disables)
     std::vector<SegSpec> segs = segs_in;
     if (aviews.empty() || aviews.size() > 4 || dviews.empty() || dviews.size() > 4 || segs.size() > CG_MAX_SEGS)
         return fail("build_gemm: bad view/segment counts");
@@ -513,9 +530,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     op.block_n = bn;
     op.halo = (conv3x3 && bn <= g_halo_max_n) ? 1 : 0;
     Tile t = choose_tile(W, H, B, 128);
-    static int box9_on = -1, bres_max = -1;
-    if (box9_on < 0) { const char* e = getenv("SDN_BOX9"); box9_on = e ? atoi(e) : 1; }
-    if (bres_max < 0) { const char* e = getenv("SDN_BRES_MAXKB"); bres_max = (e ? atoi(e) : 80) * 1024; }
+    static const int box9_on = env_int("SDN_BOX9", 1), bres_max = env_int("SDN_BRES_MAXKB", 80) * 1024;
     {
         // box9: one (TH+2)x(TW+2) box per (source, channel block) feeds all nine taps; needs the whole
         // packed weight matrix resident in shared memory and 8-pixel-wide tiles
@@ -535,8 +550,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     } else if (op.halo) {
         // one image per box and TW % 8 == 0 so the vertical-tap row shifts are whole swizzle groups
         double best = 1e300;
-        static int force_tw = -1;
-        if (force_tw < 0) { const char* e = getenv("SDN_HALO_TW"); force_tw = e ? atoi(e) : 0; }
+        static const int force_tw = env_int("SDN_HALO_TW", 0);
         for (int TW = 8; TW <= 32; TW *= 2) {
             if (force_tw && TW != force_tw) continue;
             const int TH = 128 / TW;
@@ -607,8 +621,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // weights resident in shared memory when the whole packed matrix of this N tile fits;
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
         const int b_total = kblocks * 3 * bn * op.swa;
-        static int ups_on = -1;
-        if (ups_on < 0) { const char* e = getenv("SDN_UPS"); ups_on = e ? atoi(e) : 3; }
+        static const int ups_on = env_int("SDN_UPS", 3);
         const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
         if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
@@ -650,8 +663,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     const int W = avariants[0].W, H = avariants[0].H;
     p.halo = taps == 9 ? 1 : 0;
     op.tr2_natoms = 0;
-    static int tr2_on = -1;
-    if (tr2_on < 0) { const char* e = getenv("SDN_WGRAD_TR2"); tr2_on = e ? atoi(e) : 1; }
+    static const int tr2_on = env_int("SDN_WGRAD_TR2", 1);
     if (tr2_on && p.halo && (cout == 32 || cout == 64) && W % 8 == 0 && avariants.size() == 1 && avariants[0].C == cout) {
         // levels 1-2 (small Cout, many pixels): swapped roles, one halo box per channel atom (wgrad_tr.cuh)
         const int atoms = cin_tot / CA;
@@ -679,8 +691,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
         op.tr2_natoms = natoms;
         op.tr2_ndx = ndx;
         const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
-        static int waves2 = -1;
-        if (waves2 < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves2 = e ? atoi(e) : 1; }
+        static const int waves2 = env_int("SDN_WGRAD_WAVES", 1);
         int split = std::max(1, std::min((waves2 * c->num_sms) / p.unit_groups, ptiles));
         op.grid = dim3(split, p.unit_groups, 1);
         return 0;
@@ -711,8 +722,7 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     p.a_variants = (int)avariants.size();
     p.a_atoms = cout >= 128 ? 2 : 1;
     p.m_tiles = (cout + 127) / 128;
-    static int tr_on = -1;
-    if (tr_on < 0) { const char* e = getenv("SDN_WGRAD_TR"); tr_on = e ? atoi(e) : 1; }
+    static const int tr_on = env_int("SDN_WGRAD_TR", 1);
     // measured: the swapped roles win when a unit is 64 channels wide or when there are >= 6 units
     // (two sources); 3 units of 32 channels are issue-bound either way and stay in the plain layout
     p.tr = (tr_on && p.halo && (cout == 32 || cout == 64) && (tr_on == 2 || CA == 64 || 3 * (cin_tot / CA) >= 6)) ? 1 : 0;
@@ -756,15 +766,13 @@ static int build_wgrad(sdn_ctx* c, WgradOp& op, int B, const std::vector<SrcView
     op.smem = stages * stage_bytes + 2048;
     const int ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int ctas_per_split = p.unit_groups * p.m_tiles * p.a_variants;
-    static int waves = -1;
     // one wave measured best with the current kernels (256 pairs: +1.2 %, 32 pairs: +4.6 % over two waves:
     // half the split-K partial sums to merge); the older kernels preferred two
-    if (waves < 0) { const char* e = getenv("SDN_WGRAD_WAVES"); waves = e ? atoi(e) : 1; }
+    static const int waves = env_int("SDN_WGRAD_WAVES", 1);
     // ConvTranspose2d: the four quadrant variants of a pixel tile read the SAME source tile.  With one wave
     // all four run side by side (blockIdx.z = variant, same blockIdx.x = same tiles), so the source comes from
     // DRAM once and from L2 three times; with two waves it is streamed from DRAM twice.
-    static int convt_waves = -1;
-    if (convt_waves < 0) { const char* e = getenv("SDN_CONVT_WGRAD_WAVES"); convt_waves = e ? atoi(e) : 1; }
+    static const int convt_waves = env_int("SDN_CONVT_WGRAD_WAVES", 1);
     const int w_eff = p.a_variants == 4 ? convt_waves : waves;
     int split = (w_eff * c->num_sms) / ctas_per_split;   // never spill into a partial extra wave (1 CTA per SM)
     split = std::max(1, std::min(split, ptiles));
@@ -970,7 +978,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
 // runs a partial last wave, and the tail of a 1.3-wave launch is a third of its time.
 template <typename K>
 static int occ_grid(const sdn_ctx* c, K kernel, long long work_items, int block) {
-    static std::map<const void*, int> cache;
+    static thread_local std::map<const void*, int> cache;
     const void* key = reinterpret_cast<const void*>(kernel);
     auto it = cache.find(key);
     int per_sm;
@@ -1056,7 +1064,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     if (c->pre_only) return fail("sdn_forward: context was created with SDN_CTX_PREPROCESS_ONLY");
     if (!c->have_params) return fail("sdn_forward: call sdn_set_params first");
     SDN_OK(prepare_batch(c, B));
-    g_pdl_auto = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
+    c->pdl = t_pdl = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
     if (!training && dirty) {
         // eval: scale/shift from the running statistics, folded into the weights at pack time
         for (int i = 0; i < 18; ++i) {
@@ -1107,14 +1115,16 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
         }
         GemmOp op = L.fprop;
         op.p.flags = (op.p.flags & ~CG_STATS) | CG_STATS;
+#ifdef SDN_FORENSICS
         {
-            static int dbg = -1;
-            if (dbg < 0) { const char* e = getenv("SDN_DEBUG_ABLATE"); dbg = e ? atoi(e) : 0; }
-            op.p.flags |= dbg;   // timing experiments only (results are garbage)
-            static int dbg_layer = -2;
-            if (dbg_layer == -2) { const char* e = getenv("SDN_DEBUG_TRACE_LAYER"); dbg_layer = e ? atoi(e) : -1; }
+            // timing experiments only (results are garbage): never compiled into the product library
+            static const int dbg = env_int("SDN_DEBUG_ABLATE", 0) &
+                                   (CG_DBG_NOMMA | CG_DBG_NOEPI | CG_DBG_NOLOADA | CG_DBG_NOSTORE | CG_DBG_NOSTATS);
+            op.p.flags |= dbg;
+            static const int dbg_layer = env_int("SDN_DEBUG_TRACE_LAYER", -1);
             op.p.dbg = (i == dbg_layer) ? c->dbg : nullptr;
         }
+#endif
         {
             const double px = (double)B * L.y.H * L.y.W;
             ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
@@ -1183,11 +1193,11 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
         SDN_OK(bn_backward(c, L, B, st));
     }
     {
-        static int wdbg_layer = -2;
-        if (wdbg_layer == -2) { const char* e = getenv("SDN_DEBUG_TRACE_WGRAD"); wdbg_layer = e ? atoi(e) : -1; }
+#ifdef SDN_FORENSICS
+        static const int wdbg_layer = env_int("SDN_DEBUG_TRACE_WGRAD", -1);
         L.wgrad.p.dbg = (i == wdbg_layer) ? c->dbg : nullptr;
-        static int overlap_env = -1;
-        if (overlap_env < 0) { const char* e = getenv("SDN_WGRAD_OVERLAP"); overlap_env = e ? atoi(e) : 1; }
+#endif
+        static const int overlap_env = env_int("SDN_WGRAD_OVERLAP", 1);
         // per-op profiling times kernels with events on `st`: keep everything there while it is on
         const bool overlap = overlap_env && c->side != nullptr && !c->prof && L.has_dgrad;
         cudaStream_t ws = st;
@@ -1235,8 +1245,7 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
     }
     // same overlap as the 3x3 convs: the ConvTranspose2d data gradient goes first on `st`, its weight gradient
     // (and the bias / weight unpack) run next to whatever follows on the low-priority side stream
-    static int overlap_env = -1;
-    if (overlap_env < 0) { const char* e = getenv("SDN_WGRAD_OVERLAP"); overlap_env = e ? atoi(e) : 1; }
+    static const int overlap_env = env_int("SDN_WGRAD_OVERLAP", 1);
     const bool overlap = overlap_env && c->side != nullptr && !c->prof;
     cudaStream_t ws = st;
     if (overlap) {
@@ -1295,8 +1304,8 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
     const int parts = xblocks * yblocks;
     // 3 uint8 sources read + fp32 input/target + u8 mask written per sample
     // decode+resize moves the SURVEY 8(d) bytes; the augmentation passes re-read / re-write the fp32 views
-    ProfScope* ps = new ProfScope(c, st, "pre_decode_resize", 0, 0.0,
-                                  (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
+    {
+    ProfScope ps(c, st, "pre_decode_resize", 0, 0.0, (double)B * (3.0 * Hs * Ws * 3 + (double)H * W * (6 * 4 + 4 + 1)));
     // shared-memory staged kernel when the source rows are 16-byte aligned and the footprint fits
     const int max_rows = (int)std::ceil((double)PRE_ROWS * Hs / H) + 3;
     const int row_bytes = (((int)std::ceil(128.0 * Ws / W) + 3) * 3 + 47) & ~15;
@@ -1304,12 +1313,6 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
     const bool aligned = ((Ws * 3) % 16 == 0) && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)disparity) % 16 == 0);
     const bool staged = aligned && pre_smem <= 200 * 1024 && !(flags & SDN_PREPROCESS_DIRECT);
     if (staged) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_OK(cudaFuncSetAttribute(decode_resize_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
         if (flags & SDN_RESIZE_FOURTERM)
             launch_k(decode_resize_smem_kernel<true>, dim3(parts, B), 256, pre_smem, st, 
                 left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
@@ -1327,7 +1330,7 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
                                                                     target, mask, valid_count, aug,
                                                                     aug ? gray_part : nullptr, parts);
     ++c->launches;
-    delete ps;
+    }
     if (aug != nullptr) {
         ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
         launch_k(augment_point_kernel, dim3((H * W + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug, gray_part, parts,
@@ -1342,11 +1345,83 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
 }
 
 
+
+// ------------------------------------------------------------------- NCCL
+// Resolved with dlopen at sdn_comm_init time: inside a PyTorch process "libnccl.so.2" is already mapped (torch's
+// bundled copy) and RTLD_NOLOAD returns exactly that one, so the process never holds two NCCL versions; a plain
+// C host gets the system library.  No link-time dependency: single-GPU users never need NCCL at all.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.handle != nullptr) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (h == nullptr) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) return fail("sdn_comm: cannot load libnccl.so.2 (%s)", dlerror());
+    NcclApi a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(dlsym(h, "ncclGetVersion"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+        return fail("sdn_comm: libnccl.so.2 lacks a required symbol");
+    a.handle = h;
+    g_nccl = a;
+    return 0;
+}
+#define NCCL_OK(call)                                                                                     \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// elements of parameter i in StereoUNet.parameters() order (model.py:59-77)
+static long long param_numel(const sdn_ctx* c, int i) {
+    for (int l = 0; l < 18; ++l) {
+        const ConvL& L = c->conv[l];
+        if (i == L.p_w) return 9LL * L.cin * L.cout;
+        if (i == L.p_gamma || i == L.p_beta) return L.cout;
+    }
+    for (int k = 0; k < 4; ++k) {
+        const UpL& U = c->up[k];
+        if (i == U.p_w) return 4LL * U.cin * U.cout;
+        if (i == U.p_b) return U.cout;
+    }
+    return (i == 62 || i == 64) ? 32 : 1;   // the two 1x1 heads: weight [1,32,1,1], bias [1]
+}
+
+// The gradient destinations of backward stage `stage` as ONE contiguous fp32 range (the all-reduce bucket).
+static int stage_bucket(sdn_ctx* c, int stage, float** base, long long* count) {
+    int first = 0, num = 0;
+    SDN_OK(sdn_stage_param_range(stage, &first, &num));
+    long long total = 0;
+    for (int i = first; i < first + num; ++i) {
+        if (c->grads[i] == nullptr) return fail("data-parallel step: gradient destination %d is not bound", i);
+        if (c->grads[i] != c->grads[first] + total)
+            return fail("data-parallel step: gradients %d..%d must be consecutive views of one flat buffer "
+                        "(parameters() order), parameter %d is not", first, first + num - 1, i);
+        total += param_numel(c, i);
+    }
+    *base = c->grads[first];
+    *count = total;
+    return 0;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
 
 const char* sdn_last_error(void) { return g_err.c_str(); }
-int sdn_version(void) { return 100; }
+int sdn_version(void) { return 200; }
 
 int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned flags) {
     if (out == nullptr) return fail("sdn_create: out is NULL");
@@ -1383,6 +1458,7 @@ int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned 
 int sdn_destroy(sdn_ctx* c) {
     if (c == nullptr) return 0;
     cudaSetDevice(c->device);
+    sdn_comm_destroy(c);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1416,14 +1492,14 @@ int sdn_set_params(sdn_ctx* c, const float* const* params, float* const* grads, 
 int sdn_forward(sdn_ctx* c, const float* x, float* disp, float* logvar, int B, int training, int params_dirty,
                 void* stream) {
     if (c == nullptr || x == nullptr) return fail("sdn_forward: NULL argument");
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     return forward_impl(c, x, disp, logvar, B, training, params_dirty, (cudaStream_t)stream);
 }
 
 int sdn_backward_begin(sdn_ctx* c, const float* g_disp, const float* g_logvar, int accumulate, void* stream) {
     if (c == nullptr || g_disp == nullptr) return fail("sdn_backward_begin: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     SDN_OK(backward_prologue(c, accumulate, st));
     const long long npix = (long long)c->B * c->H * c->W;
     ProfScope ps(c, st, "head_bwd", 0, 0.0, (double)npix * (64 + 8 + 64));
@@ -1441,7 +1517,7 @@ int sdn_count_valid(sdn_ctx* c, const float* target, const uint8_t* mask, int B,
     if (c == nullptr || target == nullptr || mask == nullptr || count_out == nullptr)
         return fail("sdn_count_valid: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     SDN_OK(zero_fill(c, count_out, sizeof(unsigned long long), st));
     const long long npix = (long long)B * c->H * c->W;
     launch_k(mask_count_kernel, occ_grid(c, mask_count_kernel, npix, 256), 256, 0, st, target, mask, npix, count_out);
@@ -1450,13 +1526,13 @@ int sdn_count_valid(sdn_ctx* c, const float* target, const uint8_t* mask, int B,
     return 0;
 }
 
-int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* disp, float* logvar, float* sums4,
+int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* disp, float* logvar, double* sums4,
                    unsigned long long* count, const unsigned long long* n_norm_dev, int with_backward, int accumulate,
                    void* stream) {
     if (c == nullptr || target == nullptr || mask == nullptr || sums4 == nullptr || count == nullptr)
         return fail("sdn_loss_begin: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     if (c->B < 1) return fail("sdn_loss_begin: no forward has run");
     const long long npix = (long long)c->B * c->H * c->W;
     if (with_backward) {
@@ -1495,7 +1571,7 @@ int sdn_stage_param_range(int stage, int* first, int* num) {
 int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
     if (c == nullptr) return fail("sdn_backward_stage: NULL ctx");
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     if (!c->have_forward_train) return fail("backward without a training-mode forward");
     const int B = c->B;
     switch (stage) {
@@ -1524,6 +1600,117 @@ int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
     return 0;
 }
 
+// ------------------------------------------------------------ data parallel
+int sdn_comm_unique_id(void* out128) {
+    if (out128 == nullptr) return fail("sdn_comm_unique_id: NULL argument");
+    SDN_OK(load_nccl());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+int sdn_comm_init(sdn_ctx* c, const void* id128, int rank, int world) {
+    if (c == nullptr || id128 == nullptr) return fail("sdn_comm_init: NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail("sdn_comm_init: rank %d outside world %d", rank, world);
+    if (c->comm != nullptr) return fail("sdn_comm_init: the context already has a communicator");
+    SDN_ENTER(c);
+    SDN_OK(load_nccl());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_OK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    c->comm_rank = rank; c->comm_world = world;
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_bucket, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    return 0;
+}
+
+int sdn_comm_destroy(sdn_ctx* c) {
+    if (c == nullptr) return 0;
+    if (c->comm != nullptr) {
+        cudaSetDevice(c->device);
+        if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    if (c->comm_stream) { cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr; }
+    if (c->ev_bucket) { cudaEventDestroy(c->ev_bucket); c->ev_bucket = nullptr; }
+    if (c->ev_comm) { cudaEventDestroy(c->ev_comm); c->ev_comm = nullptr; }
+    c->comm_world = 1; c->comm_rank = 0;
+    return 0;
+}
+
+int sdn_comm_world(const sdn_ctx* c) { return c ? c->comm_world : 0; }
+
+int sdn_comm_allreduce(sdn_ctx* c, void* buf, int64_t count, int dtype, void* stream) {
+    if (c == nullptr || buf == nullptr || count < 0) return fail("sdn_comm_allreduce: bad argument");
+    if (c->comm == nullptr) return c->comm_world == 1 ? 0 : fail("sdn_comm_allreduce: no communicator");
+    SDN_ENTER(c);
+    const ncclDataType_t t = dtype == SDN_F32 ? ncclFloat32 : dtype == SDN_F64 ? ncclFloat64 : ncclUint64;
+    if (dtype != SDN_F32 && dtype != SDN_F64 && dtype != SDN_U64) return fail("sdn_comm_allreduce: dtype %d", dtype);
+    NCCL_OK(g_nccl.AllReduce(buf, buf, (size_t)count, t, ncclSum, c->comm, (cudaStream_t)stream));
+    return 0;
+}
+
+// One call = the loop body of run_epoch for one assembled batch (train.py:325-342, everything but
+// optimizer.step()): forward -> valid count (all-reduced: the loss normaliser is the GLOBAL count) -> fused
+// loss + metric sums + head backward -> four backward stages, each stage's gradient bucket all-reduced on the
+// communicator stream while the next stage runs -> join.
+int sdn_train_step(sdn_ctx* c, const float* x, const float* target, const uint8_t* mask, int B, int params_dirty,
+                   double* sums4, unsigned long long* count, unsigned long long* n_norm, unsigned flags,
+                   void* stream) {
+    if (c == nullptr || x == nullptr || target == nullptr || mask == nullptr || sums4 == nullptr || count == nullptr ||
+        n_norm == nullptr)
+        return fail("sdn_train_step: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDN_ENTER(c);
+    const bool dp = c->comm != nullptr && c->comm_world > 1;
+    float* bucket[SDN_NUM_STAGES] = {};
+    long long bucket_n[SDN_NUM_STAGES] = {};
+    if (dp)
+        for (int s = 0; s < SDN_NUM_STAGES; ++s) SDN_OK(stage_bucket(c, s, &bucket[s], &bucket_n[s]));
+    SDN_OK(forward_impl(c, x, nullptr, nullptr, B, 1, params_dirty, st));
+    if (!(flags & SDN_STEP_HAVE_COUNT)) SDN_OK(sdn_count_valid(c, target, mask, B, n_norm, stream));
+    if (dp) {
+        ProfScope ps(c, st, "allreduce_count", 0, 0.0, 8.0);
+        NCCL_OK(g_nccl.AllReduce(n_norm, n_norm, 1, ncclUint64, ncclSum, c->comm, st));
+    }
+    SDN_OK(sdn_loss_begin(c, target, mask, nullptr, nullptr, sums4, count, n_norm, 1, 0, stream));
+    const bool overlap = dp && !(flags & SDN_STEP_NO_OVERLAP) && !c->prof;
+    for (int s = 0; s < SDN_NUM_STAGES; ++s) {
+        SDN_OK(sdn_backward_stage(c, s, stream));
+        if (!dp) continue;
+        cudaStream_t cs = st;
+        if (overlap) {
+            CUDA_OK(cudaEventRecord(c->ev_bucket, st));
+            CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_bucket, 0));
+            cs = c->comm_stream;
+        }
+        ProfScope ps(c, cs, "allreduce_grads", s, 0.0, (double)bucket_n[s] * 4.0);
+        NCCL_OK(g_nccl.AllReduce(bucket[s], bucket[s], (size_t)bucket_n[s], ncclFloat32, ncclSum, c->comm, cs));
+    }
+    if (overlap) {
+        CUDA_OK(cudaEventRecord(c->ev_comm, c->comm_stream));
+        CUDA_OK(cudaStreamWaitEvent(st, c->ev_comm, 0));
+    }
+    return 0;
+}
+
+// Validation / preview forward (run_epoch with optimizer=None, train.py:618; log_epoch_previews, train.py:268-272):
+// eval-mode forward + the same five metric sums, no gradient.  disp / logvar are optional outputs.
+int sdn_eval_step(sdn_ctx* c, const float* x, const float* target, const uint8_t* mask, int B, int params_dirty,
+                  float* disp, float* logvar, double* sums4, unsigned long long* count, void* stream) {
+    if (c == nullptr || x == nullptr || target == nullptr || mask == nullptr || sums4 == nullptr || count == nullptr)
+        return fail("sdn_eval_step: NULL argument");
+    SDN_ENTER(c);
+    SDN_OK(forward_impl(c, x, nullptr, nullptr, B, 0, params_dirty, (cudaStream_t)stream));
+    return sdn_loss_begin(c, target, mask, disp, logvar, sums4, count, nullptr, 0, 0, stream);
+}
+
 int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B, int Hs,
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
                    unsigned long long* valid_count, unsigned flags, void* stream) {
@@ -1533,8 +1720,8 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     if (B < 1 || B > c->maxB) return fail("sdn_preprocess: batch %d outside [1, %d]", B, c->maxB);
     if (Hs < 1 || Ws < 1) return fail("sdn_preprocess: bad source size %dx%d", Hs, Ws);
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
-    g_pdl_auto = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
+    SDN_ENTER(c);
+    c->pdl = t_pdl = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
     if (valid_count != nullptr) SDN_OK(zero_fill(c, valid_count, sizeof(unsigned long long), st));
     const AugParams* aug_all = reinterpret_cast<const AugParams*>(aug_dev);
     if (aug_all != nullptr && (flags & SDN_PREPROCESS_AUG_HOST)) {
@@ -1547,8 +1734,7 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
     // decode/resize pass and the in-place augmentation pass.  It paid while the augmentation was ALU-bound
     // at ~1100 instructions per pixel; with the special-function-unit version the extra launches cost more
     // than the DRAM round trip (chunk 16: 1.94 ms, whole batch: 1.51 ms at 256 pairs), so the default is off.
-    static int chunk_cfg = -1;
-    if (chunk_cfg < 0) { const char* e = getenv("SDN_PRE_CHUNK"); chunk_cfg = e ? atoi(e) : 0; }
+    static const int chunk_cfg = env_int("SDN_PRE_CHUNK", 0);
     const int chunk = (aug_all != nullptr && chunk_cfg > 0) ? chunk_cfg : B;
     const size_t src_img = (size_t)Hs * Ws * 3, plane = (size_t)c->H * c->W;
     const int parts = ((c->W + 127) / 128) * ((c->H + PRE_ROWS - 1) / PRE_ROWS);
@@ -1571,7 +1757,7 @@ int sdn_adamw_step(sdn_ctx* c, float* const* params, const float* const* grads, 
         return fail("sdn_adamw_step: NULL argument");
     if (n < 1 || n > 66) return fail("sdn_adamw_step: n = %d outside [1, 66]", n);
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     AdamTable t;
     long long total = 0;
     for (int i = 0; i < n; ++i) {
@@ -1594,7 +1780,7 @@ int sdn_adamw_step(sdn_ctx* c, float* const* params, const float* const* grads, 
 
 int sdn_debug_trace(sdn_ctx* c, long long* host_out) {
     if (c == nullptr || host_out == nullptr) return fail("sdn_debug_trace: NULL argument");
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(host_out, c->dbg, 3 * 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return 0;
@@ -1611,7 +1797,7 @@ int sdn_profile_enable(sdn_ctx* c, int enable) {
 // CSV "name,layer,calls,total_ms,flops,bytes" aggregated per (name, layer) since enable; resets the records.
 int sdn_profile_dump(sdn_ctx* c, char* buf, int64_t capacity) {
     if (c == nullptr || buf == nullptr || capacity < 64) return fail("sdn_profile_dump: bad argument");
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     CUDA_OK(cudaDeviceSynchronize());
     struct Agg { const char* name; int layer; int calls; double ms, flops, bytes; };
     std::vector<Agg> aggs;
@@ -1652,7 +1838,7 @@ int sdn_debug_read(sdn_ctx* c, int which, int kind, float* host_out, int64_t cap
     const size_t n = a->elems(c->B);
     dims4[0] = c->B; dims4[1] = a->H; dims4[2] = a->W; dims4[3] = a->C;
     if ((int64_t)n > capacity) return fail("sdn_debug_read: capacity %lld < %zu", (long long)capacity, n);
-    CUDA_OK(cudaSetDevice(c->device));
+    SDN_ENTER(c);
     CUDA_OK(cudaDeviceSynchronize());
     std::vector<uint16_t> tmp(n);
     CUDA_OK(cudaMemcpy(tmp.data(), a->p, n * 2, cudaMemcpyDeviceToHost));

@@ -79,7 +79,9 @@ class _Engine:
         self.packed_versions = None
         self.packed_mode = None      # "train" (plain weights + dgrad packing) or "eval" (BatchNorm folded in)
         self.grad_flat: Optional[torch.Tensor] = None
+        self.grad_views = None       # gradient destinations currently bound in the context (or None)
         self.graphs = {}             # (batch, want_logvar) -> captured eval forward
+        self.generation = 0          # bumped by every forward that overwrites the saved activations
 
     def close(self) -> None:
         if self.ctx is not None:
@@ -112,6 +114,7 @@ class _Engine:
         self.packed_versions = None
         self.packed_mode = None
         self.graphs = {}
+        self.grad_views = None
 
 
 def _ptr_array(tensors) -> ctypes.Array:
@@ -129,6 +132,12 @@ class _StereoFunction(torch.autograd.Function):
         disp, logvar = module._launch_forward(x, want_logvar, training=module.training)
         ctx.module = module
         ctx.want_logvar = want_logvar
+        # The activations, BatchNorm statistics and pool arg-max of this forward live in the ONE workspace
+        # of the module's context: a later forward overwrites them.  Stamp the generation so that a backward
+        # through a stale graph raises instead of silently differentiating the newer input.
+        eng = module._engine
+        ctx.generation = eng.generation      # _launch_forward bumped it
+        ctx.ctx_id = eng.ctx.value
         if want_logvar:
             return disp, logvar
         return disp
@@ -136,9 +145,18 @@ class _StereoFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grad_outputs):
         module = ctx.module
+        eng = module._engine
+        if eng.ctx is None or ctx.generation != eng.generation or ctx.ctx_id != eng.ctx.value:
+            raise RuntimeError(
+                "libsdn_b200 keeps the activations of ONE training forward per module: another forward ran "
+                "(or the workspace was re-created) between this graph's forward and its backward. Call "
+                "backward() before the next forward (gradient accumulation over several backward() calls is fine)."
+            )
         g_disp = grad_outputs[0]
         g_logvar = grad_outputs[1] if ctx.want_logvar else None
-        grads = module._launch_backward(g_disp, g_logvar)
+        if g_disp is None:   # only logvar was used by the loss
+            g_disp = torch.zeros_like(g_logvar)
+        grads = module._launch_backward(g_disp, g_logvar, ctx.want_logvar)
         return (None, None, None, *grads)
 
 
@@ -197,32 +215,45 @@ class StereoUNet(nn.Module):
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise ValueError(f"H and W must be multiples of 16, got {tuple(x.shape[2:])}")
 
-    def _bind(self, x: torch.Tensor) -> bool:
+    def _send_params(self) -> None:
+        """Hand the current parameter / BatchNorm-buffer / gradient-destination pointers to the context."""
+        lib = _lib.load()
+        eng = self._engine
+        params = self._param_list()
+        bns = self._bn_layers()
+        _lib.check(
+            lib.sdn_set_params(
+                eng.ctx,
+                _ptr_array(params),
+                _ptr_array(eng.grad_views) if eng.grad_views is not None else None,
+                _ptr_array([b.running_mean for b in bns]),
+                _ptr_array([b.running_var for b in bns]),
+                _ptr_array([b.num_batches_tracked for b in bns]),
+            )
+        )
+        eng.bound_ptrs = self._ptr_key()
+
+    def _ptr_key(self):
+        eng = self._engine
+        params = tuple(p.data_ptr() for p in self._param_list()) + tuple(b.running_mean.data_ptr() for b in self._bn_layers())
+        grads = None if eng.grad_views is None else tuple(None if v is None else v.data_ptr() for v in eng.grad_views)
+        return params, grads
+
+    def _bind(self, x: torch.Tensor, training: Optional[bool] = None) -> bool:
         """Make sure the context exists for this shape and points at the current
         parameter storages; returns True when the bf16 operand cache is stale."""
         eng = self._engine
         eng.ensure(x.device, x.shape[0], x.shape[2], x.shape[3])
-        params = self._param_list()
-        bns = self._bn_layers()
-        for p in params:
+        for p in self._param_list():
             if p.device != x.device or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("parameters must be contiguous fp32 tensors on the input's device")
-        ptrs = tuple(p.data_ptr() for p in params) + tuple(b.running_mean.data_ptr() for b in bns)
-        if ptrs != eng.bound_ptrs:
-            lib = _lib.load()
-            _lib.check(
-                lib.sdn_set_params(
-                    eng.ctx,
-                    _ptr_array(params),
-                    None,
-                    _ptr_array([b.running_mean for b in bns]),
-                    _ptr_array([b.running_var for b in bns]),
-                    _ptr_array([b.num_batches_tracked for b in bns]),
-                )
-            )
-            eng.bound_ptrs = ptrs
-            eng.packed_versions = None
-        dirty = self._versions() != eng.packed_versions or eng.packed_mode != ("train" if self.training else "eval")
+        key = self._ptr_key()
+        if key != eng.bound_ptrs:
+            if eng.bound_ptrs is None or key[0] != eng.bound_ptrs[0]:
+                eng.packed_versions = None       # new parameter storages: the operand cache is stale
+            self._send_params()
+        training = self.training if training is None else training
+        dirty = self._versions() != eng.packed_versions or eng.packed_mode != ("train" if training else "eval")
         return dirty
 
     def _versions(self):
@@ -231,13 +262,27 @@ class StereoUNet(nn.Module):
         return tuple(p._version for p in self._param_list()) + tuple(b.running_var._version for b in bns) + \
             tuple(b.running_mean._version for b in bns)
 
-    def _launch_forward(self, x: torch.Tensor, want_logvar: bool, training: bool, want_outputs: bool = True):
-        lib = _lib.load()
+    def _pre_forward(self, x: torch.Tensor, training: bool):
+        """Common prologue of every library forward: fp32 contiguous input, context bound to the current
+        storages.  Returns (x, dirty): dirty = the bf16 operand cache must be re-packed by this call."""
         x = x.detach()
         if x.dtype != torch.float32:
             x = x.float()
         x = x.contiguous()
-        dirty = self._bind(x)
+        dirty = self._bind(x, training)
+        self._engine.generation += 1      # this forward overwrites the activations an older graph saved
+        return x, dirty
+
+    def _post_forward(self, dirty: bool, training: bool) -> None:
+        if dirty:
+            eng = self._engine
+            eng.packed_versions = self._versions()
+            eng.packed_mode = "train" if training else "eval"
+            eng.graphs = {}
+
+    def _launch_forward(self, x: torch.Tensor, want_logvar: bool, training: bool, want_outputs: bool = True):
+        lib = _lib.load()
+        x, dirty = self._pre_forward(x, training)
         eng = self._engine
         b, _, h, w = x.shape
         disp = torch.empty((b, 1, h, w), device=x.device, dtype=torch.float32) if want_outputs else None
@@ -255,10 +300,7 @@ class StereoUNet(nn.Module):
                 stream,
             )
         )
-        if dirty:
-            eng.packed_versions = self._versions()
-            eng.packed_mode = "train" if training else "eval"
-            eng.graphs = {}
+        self._post_forward(dirty, training)
         return disp, logvar
 
     # Small-batch inference (the live viewer's per-frame call, depth_live_dl.py:518-529) is bound by
@@ -268,7 +310,7 @@ class StereoUNet(nn.Module):
     def _forward_eval_graphed(self, x: torch.Tensor, want_logvar: bool):
         eng = self._engine
         x = x.detach().float().contiguous()
-        dirty = self._bind(x)
+        dirty = self._bind(x, False)
         key = (x.shape[0], want_logvar)
         entry = None if dirty else eng.graphs.get(key)
         if entry is None:
@@ -283,6 +325,7 @@ class StereoUNet(nn.Module):
             return disp, logvar
         graph, static_x, g_disp, g_logvar = entry
         static_x.copy_(x)
+        eng.generation += 1          # the replay overwrites the workspace activations too
         graph.replay()
         return g_disp.clone(), (g_logvar.clone() if g_logvar is not None else None)
 
@@ -297,26 +340,19 @@ class StereoUNet(nn.Module):
         return flat, views
 
     def _bind_grads(self, views) -> None:
-        lib = _lib.load()
-        eng = self._engine
-        params = list(self.parameters())
-        bns = self._bn_layers()
-        _lib.check(
-            lib.sdn_set_params(
-                eng.ctx,
-                _ptr_array(params),
-                _ptr_array(views),
-                _ptr_array([b.running_mean for b in bns]),
-                _ptr_array([b.running_var for b in bns]),
-                _ptr_array([b.num_batches_tracked for b in bns]),
-            )
-        )
+        """views: 66 gradient destinations in parameters() order; None entries are not written."""
+        self._engine.grad_views = list(views)
+        self._send_params()
 
-    def _launch_backward(self, g_disp: torch.Tensor, g_logvar: Optional[torch.Tensor]):
+    def _launch_backward(self, g_disp: torch.Tensor, g_logvar: Optional[torch.Tensor], want_logvar: bool = True):
         lib = _lib.load()
         eng = self._engine
         device = g_disp.device
         flat, views = self._new_grad_views(device)
+        if not want_logvar:
+            # forward(x) without the uncertainty head: reference autograd leaves logvar_head.{weight,bias}.grad
+            # None (so AdamW skips them, no weight decay, no state) - do the same instead of dense zeros
+            views[64] = views[65] = None
         self._bind_grads(views)
         g_disp = g_disp.contiguous().float()
         g_logvar = g_logvar.contiguous().float() if g_logvar is not None else None

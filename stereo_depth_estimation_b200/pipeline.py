@@ -58,7 +58,12 @@ class SourcePrefetcher:
     def _issue(self, slot: int, batch: Sequence[torch.Tensor]) -> None:
         self._check(batch)
         if self._dev[slot] is None or any(d.shape != s.shape for d, s in zip(self._dev[slot], batch)):
-            self._dev[slot] = [torch.empty(t.shape, dtype=torch.uint8, device=self.device) for t in batch]
+            # (re)allocate ON the copy stream: the caching allocator then hands out blocks that are safe to
+            # write from that stream (a block freed by a main-stream tensor could still have kernels pending);
+            # the buffers being dropped were last read on the consumer's stream, which _freed[slot] covers
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self._freed[slot])
+                self._dev[slot] = [torch.empty(t.shape, dtype=torch.uint8, device=self.device) for t in batch]
         self.bytes_per_batch = sum(t.numel() for t in batch)
         srcs = []
         for i, t in enumerate(batch):
@@ -101,6 +106,8 @@ class SourcePrefetcher:
             main = torch.cuda.current_stream(self.device)
             main.wait_event(self._ready[cur])
             left, right, disp = self._dev[cur]
+            for t in (left, right, disp):
+                t.record_stream(main)      # allocated on the copy stream, consumed on the caller's
 
             def done(cur=cur):
                 self._freed[cur].record(torch.cuda.current_stream(self.device))

@@ -23,6 +23,7 @@ NCCL overlaps the rest of the backward.  BatchNorm statistics stay per rank
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, Iterable, Optional, Tuple
 
@@ -54,52 +55,85 @@ def stage_slices(model: StereoUNet) -> list:
 
 
 class FusedStep:
+    """Level-B2 step driver over ``sdn_train_step`` / ``sdn_eval_step`` (include/sdn.h).
+
+    ``process_group``: a ``torch.distributed`` group (any backend) used ONLY to hand rank 0's NCCL unique id
+    to the other ranks; the data path (valid-count and gradient-bucket all-reduces) runs on the library's own
+    communicator (``sdn_comm_init``) so that the buckets overlap the backward inside one C call."""
+
     def __init__(self, model: StereoUNet, optimizer: Optional[torch.optim.Optimizer] = None,
                  process_group=None, overlap: bool = True) -> None:
         self.model = model
         self.optimizer = optimizer
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist is not None and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.overlap = overlap
         self.flat = None
         self.views = None
         self.slices = None
-        self.sums = None       # device fp32 [4]: sum nll, |diff|, diff^2, exp(.5 logvar)
+        self.sums = None       # device fp64 [4]: sum nll, |diff|, diff^2, exp(.5 logvar)
         self.count = None      # device i64 [1]: valid pixels accumulated with the sums
-        self.n_norm = None     # device i64 [1]: loss normaliser of the current step
-        self.comm_stream = None
+        self.n_norm = None     # device i64 [1]: loss normaliser of the current step (global count under DP)
+        self._comm_ctx = None  # address of the sdn_ctx that holds the communicator
 
     # -------------------------------------------------------------- buffers
     def _ensure(self, device: torch.device) -> None:
-        if self.flat is not None and self.flat.device == device:
+        if self.flat is None or self.flat.device != device:
+            self.flat, self.views = self.model._new_grad_views(device)
+            self.flat.zero_()
+            self.slices = stage_slices(self.model)
+            self.sums = torch.zeros(4, device=device, dtype=torch.float64)
+            self.count = torch.zeros(1, device=device, dtype=torch.int64)
+            self.n_norm = torch.zeros(1, device=device, dtype=torch.int64)
+            # the reference loop calls optimizer.zero_grad(set_to_none=True) every step (train.py:325): re-attach
+        for p, v in zip(self.model._param_list(), self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def _ensure_comm(self) -> None:
+        """Collective: every rank calls it on its first step (and again if the context was re-created)."""
+        eng = self.model._engine
+        if self.world == 1 or self._comm_ctx == eng.ctx.value:
             return
-        self.flat, self.views = self.model._new_grad_views(device)
-        self.flat.zero_()
-        self.slices = stage_slices(self.model)
-        self.sums = torch.zeros(4, device=device, dtype=torch.float32)
-        self.count = torch.zeros(1, device=device, dtype=torch.int64)
-        self.n_norm = torch.zeros(1, device=device, dtype=torch.int64)
-        if self.world > 1:
-            self.comm_stream = torch.cuda.Stream(device=device)
-        for p, v in zip(self.model.parameters(), self.views):
-            p.grad = v
+        lib = _lib.load()
+        box = [None]
+        if self.rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(lib.sdn_comm_unique_id(raw))
+            box[0] = raw.raw
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                   group=self.group)
+        _lib.check(lib.sdn_comm_init(eng.ctx, ctypes.c_char_p(box[0]), self.rank, self.world))
+        self._comm_ctx = eng.ctx.value
 
     def reset_metrics(self) -> None:
         if self.sums is not None:
             self.sums.zero_()
             self.count.zero_()
 
-    def read_metrics(self) -> Dict[str, float]:
-        """One D2H copy of the five running sums (train.py:345-357)."""
-        s = self.sums.double().cpu()
-        n = int(self.count.cpu().item())
+    def read_metrics(self, reduce: bool = True) -> Dict[str, float]:
+        """One D2H copy of the five running sums (train.py:345-357).  Under data parallelism the sums of all
+        ranks are added first (collective: every rank must call it), so the metrics describe the global batch
+        like the single-process reference's do; ``reduce=False`` returns this rank's share."""
+        sums, count = self.sums, self.count
+        if reduce and self.world > 1 and self._comm_ctx is not None:
+            lib = _lib.load()
+            eng = self.model._engine
+            stream = torch.cuda.current_stream(sums.device).cuda_stream
+            sums, count = sums.clone(), count.clone()
+            _lib.check(lib.sdn_comm_allreduce(eng.ctx, sums.data_ptr(), 4, _lib.F64, stream))
+            _lib.check(lib.sdn_comm_allreduce(eng.ctx, count.data_ptr(), 1, _lib.U64, stream))
+        s = sums.cpu()
+        n = int(count.cpu().item())
         return {"nll": float(s[0]), "abs": float(s[1]), "sq": float(s[2]), "sigma": float(s[3]), "count": n}
 
     # ----------------------------------------------------------------- steps
     def train_step(self, batch: Dict[str, torch.Tensor], valid_count: Optional[torch.Tensor] = None) -> int:
         """One optimisation step on an already-assembled batch (the reference's sample
         format).  ``valid_count`` (device int64 [1]) may come from the preprocessing
-        kernel; otherwise it is counted here.  Returns the (global) valid count; 0 means
+        kernel (it is all-reduced IN PLACE under data parallelism); otherwise it is counted here.
+        Returns the (global) valid count; 0 means
         the step was skipped like train.py:331-332 (-1 with ``FusedAdamW``: the rule is applied on the
         device and the host never learns the count)."""
         model = self.model
@@ -108,65 +142,59 @@ class FusedStep:
         target = batch["target"].contiguous()
         mask = batch["valid_mask"].contiguous()
         device = x.device
+        model._check_input(x)
+        if target.dtype != torch.float32 or mask.dtype not in (torch.bool, torch.uint8):
+            raise ValueError("target must be float32 and valid_mask bool (the reference's sample format)")
         self._ensure(device)
         model.train(True)
-        main = torch.cuda.current_stream(device)
-        stream = main.cuda_stream
-
-        # forward (no head store: the loss kernel recomputes the 1x1 heads from dec1)
-        model._check_input(x)
-        model._launch_forward(x, True, training=True, want_outputs=False)
+        x, dirty = model._pre_forward(x, True)
         eng = model._engine
-        model._bind_grads(self.views)
-
-        if valid_count is None:
-            _lib.check(lib.sdn_count_valid(eng.ctx, target.data_ptr(), mask.data_ptr(), x.shape[0],
-                                           self.n_norm.data_ptr(), stream))
-        else:
-            torch.add(valid_count.view(1), 0, out=self.n_norm)   # a kernel, not a copy-engine transfer
-        if self.world > 1:
-            dist.all_reduce(self.n_norm, group=self.group)
-
-        _lib.check(lib.sdn_loss_begin(eng.ctx, target.data_ptr(), mask.data_ptr(), None, None, self.sums.data_ptr(),
-                                      self.count.data_ptr(), self.n_norm.data_ptr(), 1, 0, stream))
-        for stage in range(_lib.NUM_STAGES):
-            _lib.check(lib.sdn_backward_stage(eng.ctx, stage, stream))
-            if self.world > 1:
-                lo, hi = self.slices[stage]
-                bucket = self.flat[lo:hi]
-                if self.overlap:
-                    self.comm_stream.wait_stream(main)
-                    with torch.cuda.stream(self.comm_stream):
-                        dist.all_reduce(bucket, group=self.group)
-                else:
-                    dist.all_reduce(bucket, group=self.group)
-        if self.world > 1 and self.overlap:
-            main.wait_stream(self.comm_stream)
+        if eng.grad_views is None or len(eng.grad_views) != len(self.views) or \
+                any(a is not b for a, b in zip(eng.grad_views, self.views)):
+            model._bind_grads(self.views)     # (the autograd path, or a new context, had bound something else)
+        self._ensure_comm()
+        n_norm = self.n_norm if valid_count is None else valid_count.view(1)
+        if n_norm.dtype != torch.int64 or not n_norm.is_cuda:
+            raise ValueError("valid_count must be a CUDA int64 tensor [1]")
+        flags = (_lib.STEP_HAVE_COUNT if valid_count is not None else 0) | (0 if self.overlap else _lib.STEP_NO_OVERLAP)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.sdn_train_step(eng.ctx, x.data_ptr(), target.data_ptr(), mask.data_ptr(), x.shape[0],
+                                      1 if dirty else 0, self.sums.data_ptr(), self.count.data_ptr(),
+                                      n_norm.data_ptr(), flags, stream))
+        model._post_forward(dirty, True)
 
         if isinstance(self.optimizer, FusedAdamW):
             # the "no valid pixel -> skip the step" rule is evaluated on the device: no host sync at all
-            self.optimizer.step(gate=self.n_norm)
+            self.optimizer.step(gate=n_norm)
             return -1
-        n_global = int(self.n_norm.cpu().item())  # the step's only host sync
+        n_global = int(n_norm.cpu().item())  # the step's only host sync
         if n_global > 0 and self.optimizer is not None:
             self.optimizer.step()
         return n_global
 
     @torch.no_grad()
-    def eval_step(self, batch: Dict[str, torch.Tensor]) -> None:
-        """Validation forward + metric sums (run_epoch with optimizer=None, train.py:618)."""
+    def eval_step(self, batch: Dict[str, torch.Tensor], want_outputs: bool = False):
+        """Validation forward + metric sums (run_epoch with optimizer=None, train.py:618).  With
+        ``want_outputs`` also returns (disparity, logvar) like the preview path (train.py:268-272)."""
         model = self.model
         lib = _lib.load()
         x = batch["input"]
         target = batch["target"].contiguous()
         mask = batch["valid_mask"].contiguous()
+        model._check_input(x)
         self._ensure(x.device)
         model.train(False)
-        model._check_input(x)
-        model._launch_forward(x, True, training=False, want_outputs=False)
+        x, dirty = model._pre_forward(x, False)
+        b, _, h, w = x.shape
+        disp = torch.empty((b, 1, h, w), device=x.device, dtype=torch.float32) if want_outputs else None
+        logvar = torch.empty_like(disp) if want_outputs else None
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        _lib.check(lib.sdn_loss_begin(model._engine.ctx, target.data_ptr(), mask.data_ptr(), None, None,
-                                      self.sums.data_ptr(), self.count.data_ptr(), None, 0, 0, stream))
+        _lib.check(lib.sdn_eval_step(model._engine.ctx, x.data_ptr(), target.data_ptr(), mask.data_ptr(), b,
+                                     1 if dirty else 0, disp.data_ptr() if disp is not None else None,
+                                     logvar.data_ptr() if logvar is not None else None, self.sums.data_ptr(),
+                                     self.count.data_ptr(), stream))
+        model._post_forward(dirty, False)
+        return (disp, logvar) if want_outputs else None
 
 
 def _metrics(tot: Dict[str, float]) -> Dict[str, float]:
