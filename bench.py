@@ -9,16 +9,22 @@ augmentations on, at 1/2/4/8 B200 (strong scaling: each rank takes 256/N pairs).
 One step = device input pipeline on raw uint8 540x960 sources (decode + resize +
 rescale + L/R augmentation) -> U-Net forward (train-mode BatchNorm) -> fused
 heteroscedastic loss -> backward (dgrad + wgrad + BN) -> bucketed NCCL
-all-reduce -> AdamW.  Nothing is skipped or cached inside the timed region.
+all-reduce (inside the library, overlapped with the backward) -> AdamW.  Nothing is
+skipped or cached inside the timed region.
 
   value : whole-job pairs/s with the uint8 sources resident in HBM.
   e2e   : the same step fed from PINNED HOST buffers (double-buffered H2D of the
           step's sources inside the timed region) plus a D2H read of the step's
           metric sums, through the package's public API.
-  roofline     : dominant kernel family, measured live with CUDA events
-                 (sdn_profile_*), algorithmic FLOPs / bytes from SURVEY 8(d).
-  cpu_baseline : the oracle port of the reference train step on the host cores.
-  --impl reference : the reference's own CPU path (oracle port, torch CPU fp32).
+  roofline     : the conv_fprop family (largest tensor-core family; FIXED so that the line reports the same
+                 kernel at every N), measured live with CUDA events (sdn_profile_*), algorithmic FLOPs / bytes
+                 from SURVEY 8(d); `rooflines` lists every family the same way.
+  dp_check     : (N > 1) the all-reduced flat gradient is bit-identical on all ranks and equals the
+                 non-overlapped all-reduce of the same step.
+  side_configs : (N = 1) BASELINE.json configs 4 and 5 and the torch-eager (cuDNN) bars on the same GPU,
+                 the latter through the UNMODIFIED reference model from baseline/_ref.
+  cpu_baseline : the reference's own run_epoch (baseline/_ref, train.py:292-418) on the host cores.
+  --impl reference : the same, K steps.
 """
 from __future__ import annotations
 
@@ -40,8 +46,11 @@ H, W = 240, 320
 HS, WS = 540, 960
 GLOBAL_BATCH = 256
 TRAIN_FLOPS_PER_PAIR = 85.024e9   # SURVEY 8(d) / BASELINE.md section 3
+FWD_FLOPS = {(240, 320): 28.430e9, (480, 640): 113.718e9, (720, 1280): 341.154e9}
+PRE_BYTES_PER_SAMPLE = 6_892_800
 METRIC = "train_pairs_per_s_240x320"
 UNIT = "pairs/s"
+ROOFLINE_FAMILY = "conv_fprop"
 
 
 def parse_args():
@@ -53,6 +62,7 @@ def parse_args():
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-latency", action="store_true", help="skip the single-pair latency probe")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip configs 4/5 and the torch-eager bars")
     ap.add_argument("--profile-out", default="", help="write the per-op table (JSON) here")
     return ap.parse_args()
 
@@ -76,40 +86,70 @@ def synth_batch_cpu(b: int, seed: int = 42):
     return {"input": x, "target": t, "valid_mask": t > 0.0}
 
 
-def cpu_train_steps(steps: int, warmup: int, batch: int = 8):
-    """The reference loop body (train.py:320-357 + AdamW) restated in oracle/ and run
-    with every host thread torch will use.  Returns (pairs/s, ms/step, threads)."""
-    from oracle import stereo_oracle as so
+def load_reference():
+    """The vendored, unmodified reference (baseline/_ref) with a no-op mlflow; None when it is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refenv
 
+        if not refenv.available():
+            return None
+        train, model_mod, _ = refenv.load(fresh=True)
+        return train, model_mod
+    except Exception:
+        return None
+
+
+def cpu_train_steps(steps: int, warmup: int, batch: int = 8):
+    """K timed steps of the reference loop body on the host cores (config 1: batch 8, 6x240x320, fp32,
+    --device cpu) after W untimed ones.  Preferred: the reference's OWN run_epoch (train.py:292-418) on its
+    own StereoUNet and torch AdamW from baseline/_ref (kind "reference"); when that copy is absent, the oracle
+    port of the same loop (kind "port").  Returns (pairs/s, ms/step, threads, kind)."""
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    data = synth_batch_cpu(batch)
+    ref = load_reference()
+    if ref is not None:
+        train, model_mod = ref
+        torch.manual_seed(42)
+        model = model_mod.StereoUNet(in_channels=6, out_channels=1)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)    # train.py:578
+        dev = torch.device("cpu")
+        if warmup > 0:
+            train.run_epoch(model, [data] * warmup, dev, optimizer=opt, global_step=0, log_every_batches=None)
+        t0 = time.perf_counter()
+        train.run_epoch(model, [data] * steps, dev, optimizer=opt, global_step=0, log_every_batches=None)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+        return batch / dt, dt * 1e3, torch.get_num_threads(), "reference"
+    from oracle import stereo_oracle as so
+
     sd = so.init_state_dict(42)
     opt = so.AdamWState()
-    data = synth_batch_cpu(batch)
     for _ in range(warmup):
         so.train_step(sd, data, opt)
     t0 = time.perf_counter()
     for _ in range(steps):
         so.train_step(sd, data, opt)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return batch / dt, dt * 1e3, torch.get_num_threads()
+    return batch / dt, dt * 1e3, torch.get_num_threads(), "port"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
-    pps, ms, threads = cpu_train_steps(steps, warm, 8)
-    sample = "oracle port of train.py:320-357 (fwd+bwd+loss+AdamW), fp32, batch 8 of 6x240x320 per step, " \
-             "input pipeline excluded (the reference overlaps it in DataLoader workers)"
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    pps, ms, threads, kind = cpu_train_steps(steps, warm, 8)
+    what = "the reference's own run_epoch (baseline/_ref, train.py:292-418) on its StereoUNet + torch AdamW" \
+        if kind == "reference" else "oracle port of train.py:320-357 (fwd+bwd+loss+AdamW)"
+    sample = f"{what}, fp32, batch 8 of 6x240x320 per step (BASELINE.json config 1), {threads} threads, input " \
+             "pipeline excluded (the reference overlaps it in DataLoader workers)"
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C1: U-Net stereo train step, 6x240x320, batch 8, host CPU (reference --device cpu path)"},
-        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,17 +245,144 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- GPU arm
-def synth_sources(b: int, seed: int, pinned: bool):
+def synth_sources(b: int, seed: int, pinned: bool, hs: int = HS, ws: int = WS):
     """uint8 HWC sources; disparity R channel in [0,3] and ~10 % invalid."""
     rng = np.random.default_rng(seed)
-    L = rng.integers(0, 256, (b, HS, WS, 3), dtype=np.uint8)
-    R = rng.integers(0, 256, (b, HS, WS, 3), dtype=np.uint8)
-    D = rng.integers(0, 256, (b, HS, WS, 3), dtype=np.uint8)
-    D[..., 0] = rng.integers(0, 4, (b, HS, WS), dtype=np.uint8)
-    D[rng.random((b, HS, WS)) < 0.1] = 0
+    L = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    R = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    D = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    D[..., 0] = rng.integers(0, 4, (b, hs, ws), dtype=np.uint8)
+    D[rng.random((b, hs, ws)) < 0.1] = 0
     out = [torch.from_numpy(a) for a in (L, R, D)]
     if pinned:
         out = [t.pin_memory() for t in out]
+    return out
+
+
+def timed_ms(fn, warm: int, iters: int) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def family_rooflines(fam: dict, peaks: dict) -> list:
+    """One entry per kernel family of the train step, same arithmetic as `roofline`."""
+    out = []
+    for name, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        if v["ms"] <= 0:
+            continue
+        if v["flops"] > 0:
+            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            out.append({"kernel": name, "bound": "tensor", "ms_per_step": v["ms"], "launches_per_step": v["calls"],
+                        "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["bf16_tflops_sustained"],
+                        "hbm_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+        elif v["bytes"] > 0:
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            out.append({"kernel": name, "bound": "hbm", "ms_per_step": v["ms"], "launches_per_step": v["calls"],
+                        "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]})
+    return out
+
+
+def side_configs(dev, peaks) -> dict:
+    """BASELINE.json configs 4 and 5 plus the torch-eager (cuDNN) bars on this GPU (rank 0, N = 1)."""
+    from stereo_depth_estimation_b200 import StereoUNet
+    from stereo_depth_estimation_b200.preprocess import AugmentSampler, DevicePreprocessor
+    from stereo_depth_estimation_b200.step import FusedStep
+
+    out = {}
+    # ---- C4: input pipeline only, 540x960 -> 240x320, batch 512 (2.39 GB of sources: larger than L2)
+    B = 512
+    src = [t.to(dev) for t in synth_sources(B, 7, pinned=False)]
+    pre = DevicePreprocessor(dev, B, (H, W))
+    sampler = AugmentSampler(seed=0)
+    buf = {"o": None}
+
+    def run_pre(aug):
+        buf["o"] = pre(src[0], src[1], src[2], aug=sampler.sample_packed(B) if aug else None, out=buf["o"])
+
+    for aug in (False, True):
+        ms = timed_ms(lambda: run_pre(aug), 3, 10)
+        gbs = B * PRE_BYTES_PER_SAMPLE / ms / 1e6
+        out["C4_input_pipeline_b512_" + ("aug" if aug else "noaug")] = {
+            "ms_per_batch": ms, "samples_per_s": B / ms * 1e3, "algorithmic_GBps": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]}
+    del src, buf
+    pre.close()
+    torch.cuda.empty_cache()
+    # ---- C5: batched inference at scaled resolutions (batch 32)
+    torch.manual_seed(0)
+    model = StereoUNet().to(dev).eval()
+    for (h, w) in ((240, 320), (480, 640), (720, 1280)):
+        x = torch.rand(32, 6, h, w, device=dev)
+        with torch.inference_mode():
+            ms = timed_ms(lambda: model(x, return_uncertainty=True), 3, 10)
+        tf = 32 * FWD_FLOPS[(h, w)] / ms / 1e9
+        out[f"C5_infer_b32_{h}x{w}"] = {"ms_per_batch": ms, "pairs_per_s": 32 / ms * 1e3, "tflops": tf,
+                                        "frac_of_sustained_bf16": tf / peaks["bf16_tflops_sustained"]}
+        del x
+        model._engine.close()
+        torch.cuda.empty_cache()
+    # ---- this path at batch 64 on a pre-assembled batch (like-for-like with the eager bars below)
+    torch.manual_seed(0)
+    model = StereoUNet().to(dev)
+    step = FusedStep(model, torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4))
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(64, 6, H, W, generator=g).to(dev)
+    t = (torch.rand(64, 1, H, W, generator=g) * 2).to(dev)
+    batch = {"input": x, "target": t, "valid_mask": t > 0.2}
+    ms = timed_ms(lambda: step.train_step(batch), 3, 10)
+    out["b200_train_b64_preassembled"] = {"ms_per_step": ms, "pairs_per_s": 64 / ms * 1e3}
+    model._engine.close()
+    del model, step
+    torch.cuda.empty_cache()
+    # ---- torch-eager bars: the UNMODIFIED reference model + loss (baseline/_ref) on this GPU
+    ref = load_reference()
+    if ref is None:
+        out["torch_eager"] = {"unavailable": "baseline/_ref not vendored"}
+        return out
+    train, model_mod = ref
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(42)
+        rmodel = model_mod.StereoUNet(in_channels=6, out_channels=1).to(dev)
+        ropt = torch.optim.AdamW(rmodel.parameters(), lr=1e-3, weight_decay=1e-4)
+        mask = batch["valid_mask"]
+        for autocast in (False, True):
+            def eager_step():
+                # loop body of train.py:325-343
+                ropt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    pred, lv = rmodel(x, return_uncertainty=True)
+                diff = pred.float()[mask] - t[mask]
+                mlv = lv.float()[mask]
+                loss = (diff.abs() * torch.exp(-mlv) + mlv).mean()
+                loss.backward()
+                ropt.step()
+
+            rmodel.train()
+            ms = timed_ms(eager_step, 2, 5)
+            out["torch_eager_train_b64_" + ("bf16_autocast" if autocast else "fp32")] = {
+                "ms_per_step": ms, "pairs_per_s": 64 / ms * 1e3}
+            rmodel.eval()
+            x1 = x[:1]
+
+            def eager_infer():
+                with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    rmodel(x1, return_uncertainty=True)
+
+            ms = timed_ms(eager_infer, 10, 100)
+            out["torch_eager_infer_1pair_" + ("bf16_autocast" if autocast else "fp32")] = {"ms": ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     return out
 
 
@@ -240,6 +407,7 @@ def run_b200(args):
     b_local = args.global_batch // world
     if b_local * world != args.global_batch:
         raise SystemExit("global batch must divide by the number of GPUs")
+    warmup = max(args.warmup, 3)
 
     torch.manual_seed(42)
     model = StereoUNet().to(dev)
@@ -272,7 +440,7 @@ def run_b200(args):
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         one_step(srcs_dev)
     barrier()
     launches0 = model.launch_count() + pre.launch_count()
@@ -305,7 +473,7 @@ def run_b200(args):
     # the bulk copy alone (no overlap), for the record
     tmp = [torch.empty_like(t, device=dev) for t in srcs_host]
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
+    barrier()
     c0.record()
     for dst, src in zip(tmp, srcs_host):
         dst.copy_(src, non_blocking=True)
@@ -327,7 +495,7 @@ def run_b200(args):
                 e0.record(main)
             one_step((left, right, disp_src))
             done()
-            packed = torch.cat([step.sums.double(), step.count.double()])
+            packed = torch.cat([step.sums, step.count.double()])
             snaps[slot].copy_(packed, non_blocking=True)
             snap_ev[slot].record(main)
             if i > 0:                          # host-side read of the previous step's result
@@ -342,6 +510,40 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = args.global_batch / (e2e_ms * 1e-3)
+
+    # ---- DP check (N > 1): all-reduced gradients identical on all ranks; overlapped == main-stream ----
+    dp_check = None
+    if world > 1:
+        def grad_of_step(overlap: bool) -> torch.Tensor:
+            step.overlap = overlap
+            saved_opt, step.optimizer = step.optimizer, None     # gradients only: identical weights for both legs
+            try:
+                pre(srcs_dev[0], srcs_dev[1], srcs_dev[2], aug=fixed_aug, out=out, count_out=count)
+                step.train_step(out, valid_count=count)
+            finally:
+                step.optimizer = saved_opt
+            torch.cuda.synchronize(dev)
+            return step.flat.clone()
+
+        fixed_aug = sampler.sample_packed(b_local)
+        g_ov = grad_of_step(True)
+        g_main = grad_of_step(False)
+        step.overlap = True
+        digest = torch.stack([g_ov.double().sum(), g_ov.double().abs().sum(), g_ov.double().pow(2).sum()])
+        parts = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(parts, digest)
+        first = [torch.empty_like(g_ov[:4096]) for _ in range(world)]
+        dist.all_gather(first, g_ov[:4096].contiguous())
+        diff = float((g_ov.double() - g_main.double()).norm() / g_main.double().norm().clamp(min=1e-30))
+        dp_check = {
+            "grad_digest_identical_on_all_ranks": bool(all(torch.equal(parts[0], p) for p in parts[1:])
+                                                       and all(torch.equal(first[0], f) for f in first[1:])),
+            "overlapped_vs_mainstream_allreduce_rel": diff,
+            "ok": bool(all(torch.equal(parts[0], p) for p in parts[1:]) and diff < 1e-5),
+            "note": "same step twice (fixed augmentation parameters, no optimizer step); the only run-to-run "
+                    "difference is the order of the fp32 wgrad atomics (~1e-7); see tests/gpu_dp_parity.py for the "
+                    "comparison with the single-process gradient",
+        }
 
     # ---- per-op roofline (separate, profiled steps; CUDA events per op) -----
     peaks = load_peaks()
@@ -359,36 +561,29 @@ def run_b200(args):
         f["ms"] += r["ms"] / prof_steps; f["flops"] += r["flops"] / prof_steps
         f["bytes"] += r["bytes"] / prof_steps; f["calls"] += r["calls"] // prof_steps
     total_prof_ms = sum(f["ms"] for f in fam.values())
-    dominant = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    dname, d = dominant
-    if d["flops"] > 0:
-        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"kernel": dname, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)"}
-    else:
-        achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roof = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+    rooflines = family_rooflines(fam, peaks)
+    dname = ROOFLINE_FAMILY if ROOFLINE_FAMILY in fam else max(fam.items(), key=lambda kv: kv[1]["ms"])[0]
+    d = fam[dname]
+    achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    roof = {"kernel": dname, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+            "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)",
+            "selection": "fixed family (the 18 conv3x3 forward launches of sdn::conv_gemm_kernel): the largest "
+                         "tensor-core family; every other family is in `rooflines`"}
     # DRAM traffic per launch of that kernel family from the committed ncu --set full capture (profiles/)
-    try:
-        src = "r1_ncu_full_step_b256_summary.json"
-        with open(os.path.join(ROOT, "profiles", src)) as f:
-            cap = json.load(f)
-        if dname == "bn_bwd" and b_local == 256:
-            fam_cap = cap["families"]["bn_bwd"]
-            roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["layers_captured"]
-            roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the" \
-                                     " reduce + apply kernels, averaged over the 18 layers of one step)"
-            roof["algorithmic_bytes_per_launch"] = d["bytes"] / max(d["calls"], 1)
-        elif dname == "conv_fprop" and b_local == 256:
+    for src in ("r2_ncu_full_step_b256_summary.json", "r1_ncu_full_step_b256_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", src)) as f:
+                cap = json.load(f)
             fam_cap = cap["families"]["forward_conv(fprop+convT_fprop)"]
-            roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["launches"]
-            roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the" \
-                                     " 22 forward conv_gemm launches of one step = 18 conv fprop + 4 ConvTranspose2d fprop)"
-            roof["algorithmic_bytes_per_launch"] = fam_cap["algorithmic_bytes"] / fam_cap["launches"]
-    except Exception:
-        pass
+            if b_local == 256:
+                roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["launches"]
+                roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum" \
+                                         " of the 22 forward conv_gemm launches of one step = 18 conv fprop + 4 ConvTranspose2d fprop)"
+                roof["algorithmic_bytes_per_launch"] = fam_cap["algorithmic_bytes"] / fam_cap["launches"]
+            break
+        except Exception:
+            continue
     roof["share_of_step"] = d["ms"] / total_prof_ms if total_prof_ms > 0 else None
     roof["launches_per_step"] = d["calls"]
     families = {k: {"ms_per_step": v["ms"],
@@ -425,21 +620,34 @@ def run_b200(args):
                 e2e_us.append((time.perf_counter() - t0) * 1e6)
         latency = {"device_p50_us": float(np.percentile(dev_us, 50)), "device_p99_us": float(np.percentile(dev_us, 99)),
                    "e2e_p50_us": float(np.percentile(e2e_us, 50)), "e2e_p99_us": float(np.percentile(e2e_us, 99)),
-                   "what": "1x6x240x320 eval forward, disparity+logvar; e2e adds 1.84 MB H2D + 2x307 KB D2H"}
+                   "what": "C2: 1x6x240x320 eval forward, disparity+logvar; e2e adds 1.84 MB H2D + 2x307 KB D2H"}
         model.train()
 
-    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------
+    # ---- side configs + CPU baseline (rank 0, N = 1 only) -------------------
+    side = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        pps, ms, threads = cpu_train_steps(3, 1, 8)
-        cpu = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 steps of the oracle train step (fwd+bwd+loss+AdamW, fp32) on batch 8 of 6x240x320, "
-                         f"{ms:.0f} ms/step"}
+    if rank == 0 and world == 1:
+        if not args.no_side_configs:
+            # free the train-step workspace first (45 GB at batch 256): config 5 needs 67 GB of its own
+            model._engine.close()
+            pre.close()
+            del srcs_dev
+            out = None
+            torch.cuda.empty_cache()
+            try:
+                side = side_configs(dev, peaks)
+            except Exception as exc:   # a side measurement must never cost the headline line
+                side = {"error": repr(exc)[:300]}
+        if not args.no_cpu_baseline:
+            pps, ms, threads, kind = cpu_train_steps(3, 1, 8)
+            cpu = {"value": pps, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": "3 timed steps (1 warm-up) of the reference train loop body (run_epoch, train.py:292-418: "
+                             f"fwd+bwd+loss+AdamW, fp32) on batch 8 of 6x240x320, {ms:.0f} ms/step"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "C3: DP train step 240x320, global batch %d (%d/GPU), augment on, raw uint8 "
                                    "540x960 sources -> preprocess -> fwd -> loss -> bwd -> allreduce -> AdamW"
@@ -453,9 +661,12 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": roof,
+            "rooflines": rooflines,
             "kernel_families": families,
+            "dp_check": dp_check,
             "cpu_baseline": cpu,
             "latency": latency,
+            "side_configs": side,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -159,8 +159,9 @@ int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, cons
                    unsigned long long* valid_count, unsigned flags, void* stream);
 
 /* Test / debug access to the NHWC bf16 activations of the last forward:
- * which = conv layer index 0..17; kind 0 = pre-BN conv output, 1 = post
- * BN+ReLU, 2 = gradient w.r.t. the pre-BN output (after backward).
+ * which = conv layer index 0..17 (100..103: the ConvTranspose2d outputs); kind 0 = pre-BN conv output, 1 = post
+ * BN+ReLU, 2 = gradient w.r.t. the pre-BN output (after backward), 3 = gradient w.r.t. the post-ReLU output,
+ * 4 / 5 (pooled layers 1, 3, 5, 7) = gradient w.r.t. / value of the 2x2 max-pooled output.
  * Copies to a host fp32 buffer of B*H_l*W_l*C_l elements; returns the dims. */
 int sdn_debug_read(sdn_ctx* ctx, int which, int kind, float* host_out, int64_t capacity, int* dims4);
 

@@ -1827,7 +1827,8 @@ int sdn_debug_read(sdn_ctx* c, int which, int kind, float* host_out, int64_t cap
     const Act* a = nullptr;
     if (which >= 0 && which < 18) {
         ConvL& L = c->conv[which];
-        a = kind == 0 ? &L.y : kind == 1 ? &L.a : kind == 2 ? &L.dy : kind == 3 ? &L.ga : nullptr;
+        a = kind == 0 ? &L.y : kind == 1 ? &L.a : kind == 2 ? &L.dy : kind == 3 ? &L.ga
+            : (kind == 4 && L.pooled_out) ? &L.gp : (kind == 5 && L.pooled_out) ? &L.pool : nullptr;
     } else if (which >= 100 && which < 104) {
         UpL& U = c->up[which - 100];
         a = kind == 0 ? &U.u : kind == 3 ? &U.gu : nullptr;

@@ -187,6 +187,103 @@ def test_forward_eval_matches_oracle(dev, b, h, w):
     assert disp.min().item() >= 0.0 and logvar.min().item() >= -6.0 and logvar.max().item() <= 3.0
 
 
+def test_forward_eval_graph_replay_matches_oracle(dev):
+    """The live viewer's per-frame call (depth_live_dl.py:518-529) replays a CUDA graph from the SECOND call
+    per (batch, want_logvar) on; the replayed outputs - not only the eager first call - must match."""
+    model, sd = fresh_model(dev)
+    model.eval()
+    for want in (True, False):
+        for call in range(3):
+            x = make_batch(dev, 1, 240, 320, seed=500 + call)["input"]
+            with torch.inference_mode():
+                out = model(x, return_uncertainty=want)
+            if want:
+                assert (1, True) in model._engine.graphs
+            rd, rl = so.model_forward(sd, x, False, True)
+            disp, logvar = out if want else (out, None)
+            assert (disp - rd).abs().max().item() / rd.abs().max().item() <= 1e-2, (want, call)
+            if want:
+                assert (logvar - rl).abs().max().item() / rl.abs().max().item() <= 1e-2, (want, call)
+    # a weight update invalidates the captured graphs (the operand cache is re-packed)
+    with torch.no_grad():
+        model.disparity_head.bias.add_(1.0)
+    x = make_batch(dev, 1, 240, 320, seed=510)["input"]
+    sd2 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for call in range(2):
+        with torch.inference_mode():
+            disp = model(x)
+        rd, _ = so.model_forward(sd2, x, False, True)
+        assert (disp - rd).abs().max().item() / rd.abs().max().item() <= 1e-2, call
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 480, 640), (1, 720, 1280), (32, 240, 320)])
+def test_forward_eval_scaled_resolutions(dev, b, h, w):
+    """BASELINE.json config 5 shapes (480x640, 720x1280) and a batch beyond the CUDA-graph limit."""
+    model, sd = fresh_model(dev)
+    x = make_batch(dev, b, h, w, seed=77)["input"]
+    model.eval()
+    with torch.inference_mode():
+        disp, logvar = model(x, return_uncertainty=True)
+    rd, rl = so.model_forward(sd, x, False, True)
+    e_d = (disp - rd).abs().max().item() / rd.abs().max().item()
+    e_l = (logvar - rl).abs().max().item() / rl.abs().max().item()
+    print(f"eval {b}x{h}x{w}: disparity max-rel {e_d:.2e} logvar max-rel {e_l:.2e}")
+    assert e_d <= 1e-2 and e_l <= 1e-2
+
+
+def test_forward_train_batch32_full_resolution(dev):
+    """The per-GPU batch of the 8-GPU run (32 x 240 x 320), train mode, vs the fp32 oracle on the same GPU."""
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, 32, 240, 320, seed=78)
+    model.train()
+    with torch.no_grad():
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+    rd, rl = so.model_forward(sd, batch["input"], True, True, {})
+    m_d = (disp - rd).abs().max().item() / rd.abs().max().item()
+    m_l = (logvar - rl).abs().max().item() / rl.abs().max().item()
+    loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
+    rloss, _ = so.loss_and_sums(rd, rl, batch["target"], batch["valid_mask"])
+    e_loss = abs(loss.item() - rloss.item()) / abs(rloss.item())
+    print(f"train 32x240x320: rel-L2 disp {rel(disp, rd):.2e} logvar {rel(logvar, rl):.2e}; "
+          f"max-normalised disp {m_d:.2e} logvar {m_l:.2e}; loss rel {e_loss:.2e}")
+    assert rel(disp, rd) <= 1e-2 and rel(logvar, rl) <= 1e-2 and e_loss <= 1e-3
+
+
+def test_eval_step_same_weights_matches_oracle(dev):
+    """Row N2: validation path (run_epoch with optimizer=None, train.py:618) - eval-mode forward + the five
+    metric sums - against the oracle at IDENTICAL weights and non-trivial BatchNorm buffers."""
+    from stereo_depth_estimation_b200.step import FusedStep, run_epoch
+
+    model, sd = fresh_model(dev)
+    batches = [make_batch(dev, 3, 64, 96, seed=900 + i) for i in range(3)]
+    model.train()
+    with torch.no_grad():
+        for b_ in batches:
+            model(b_["input"])                      # three BatchNorm buffer updates
+    cur = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    step = FusedStep(model, optimizer=None)
+    step._ensure(dev)
+    step.reset_metrics()
+    tot = {"nll": 0.0, "abs": 0.0, "sq": 0.0, "sigma": 0.0, "count": 0}
+    for b_ in batches:
+        disp, logvar = step.eval_step(b_, want_outputs=True)
+        rd, rl = so.model_forward(cur, b_["input"], False, True)
+        assert (disp - rd).abs().max().item() / rd.abs().max().item() <= 1e-2
+        assert (logvar - rl).abs().max().item() / rl.abs().max().item() <= 1e-2
+        _, sums = so.loss_and_sums(rd, rl, b_["target"], b_["valid_mask"])
+        for k in tot:
+            tot[k] += sums[k]
+    got = step.read_metrics()
+    assert got["count"] == tot["count"]
+    for k in ("nll", "abs", "sq", "sigma"):
+        assert got[k] == pytest.approx(tot[k], rel=2e-3), k
+    val, _ = run_epoch(model, batches, dev, optimizer=None)
+    oval = so.run_epoch(cur, batches, None)
+    for k in ("loss", "mae", "rmse", "sigma"):
+        assert val[k] == pytest.approx(oval[k], rel=2e-3), k
+    assert torch.equal(model.state_dict()["enc1.block.1.running_mean"], cur["enc1.block.1.running_mean"])
+
+
 def test_forward_eval_golden_fixture(dev):
     """model.npz was produced by the real reference (seed 42, trained-one-step BN buffers)."""
     f = np.load(os.path.join(GOLDEN, "model.npz"))
@@ -274,11 +371,19 @@ def test_backward_kernels_isolated(dev):
                 k = (i - 10) // 2
                 c = gu[k].shape[1]
                 assert rel(gu[k], gin[:, :c]) < 6e-3 and rel(ga[7 - 2 * k], gin[:, c:]) < 6e-3, f"dgrad {i}"
-        if i not in (1, 3, 5, 7):  # pooled outputs: arg-max ties on bf16 values, checked end to end
-            yy = y[i].clone().requires_grad_(True)
-            z = F.batch_norm(yy, None, None, params[bnname(i) + ".weight"], params[bnname(i) + ".bias"], True, 0.1, 1e-5)
-            (F.relu(z) * ga[i]).sum().backward()
-            assert rel(dy[i], yy.grad) < 6e-3, f"bn backward {i}"
+        yy = y[i].clone().requires_grad_(True)
+        z = F.batch_norm(yy, None, None, params[bnname(i) + ".weight"], params[bnname(i) + ".bias"], True, 0.1, 1e-5)
+        g_total = ga[i]
+        if i in (1, 3, 5, 7):
+            # pooled block outputs (model.py:83-86): the gradient of the pooled tensor is routed to the FIRST
+            # maximum of each 2x2 quad of the bf16 activation the consumers saw (nn.MaxPool2d backward); torch's
+            # own max_pool2d on that same activation gives the routing indices, ties included
+            gp = _nchw(model, i, 4, dev)
+            pooled, idx = F.max_pool2d(a[i], 2, return_indices=True)
+            assert torch.equal(pooled, _nchw(model, i, 5, dev)), f"maxpool forward {i}"
+            g_total = ga[i] + F.max_unpool2d(gp, idx, 2, output_size=a[i].shape[-2:])
+        (F.relu(z) * g_total).sum().backward()
+        assert rel(dy[i], yy.grad) < 6e-3, f"bn backward {i}"
     for k in range(4):
         lvl = 4 - k
         wt, bt = params[f"up{lvl}.weight"], params[f"up{lvl}.bias"]
@@ -289,14 +394,22 @@ def test_backward_kernels_isolated(dev):
         assert rel(ga[9 + 2 * k], src.grad) < 6e-3
 
 
-def test_gradients_no_worse_than_torch_bf16_autocast(dev):
+@pytest.mark.parametrize("path", ["module", "fused_step"])
+def test_gradients_no_worse_than_torch_bf16_autocast(dev, path):
+    """End-to-end gradients of BOTH entry points (autograd module path; FusedStep = sdn_train_step with the
+    in-kernel loss seed) against the fp32 ORACLE, with torch's own bf16-autocast drift as the yardstick."""
     b, h, w = 4, 128, 160
     model, sd = fresh_model(dev)
     batch = make_batch(dev, b, h, w)
     model.train()
-    disp, logvar = model(batch["input"], return_uncertainty=True)
-    loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
-    loss.backward()
+    if path == "module":
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+        loss, _ = so.loss_and_sums(disp, logvar, batch["target"], batch["valid_mask"])
+        loss.backward()
+    else:
+        from stereo_depth_estimation_b200.step import FusedStep
+
+        assert FusedStep(model, optimizer=None).train_step(batch) > 0
     ours = {k: p.grad.clone() for k, p in model.named_parameters()}
     grads = {}
     for mode in ("fp32", "bf16"):
@@ -308,14 +421,37 @@ def test_gradients_no_worse_than_torch_bf16_autocast(dev):
         rloss, _ = so.loss_and_sums(rd.float(), rl.float(), batch["target"], batch["valid_mask"])
         rloss.backward()
         grads[mode] = {k: v.grad for k, v in leaves.items()}
+    worst = (0.0, 0.0, "")
     for k in ours:
         e_ours = rel(ours[k], grads["fp32"][k])
         e_torch = rel(grads["bf16"][k], grads["fp32"][k])
+        worst = max(worst, (e_ours, e_torch, k))
         assert e_ours <= 1.5 * e_torch + 2e-2, (k, e_ours, e_torch)
         cos = F.cosine_similarity(ours[k].flatten().double(), grads["fp32"][k].flatten().double(), dim=0).item()
         assert cos > 0.8, (k, cos)
+    print(f"[{path}] worst gradient rel-L2 vs fp32 oracle: ours {worst[0]:.3e} torch-bf16-autocast {worst[1]:.3e} ({worst[2]})")
     for k in ("disparity_head.weight", "logvar_head.weight", "dec1.block.4.weight", "dec1.block.4.bias"):
         assert rel(ours[k], grads["fp32"][k]) < 2e-2, k
+
+
+def test_autograd_contract_matches_reference_semantics(dev):
+    """(1) a backward through a graph whose activations were overwritten by a later forward raises instead of
+    returning gradients of the newer input; (2) forward(x) without the uncertainty head leaves
+    logvar_head.{weight,bias}.grad None, like reference autograd (so AdamW skips them)."""
+    model, _ = fresh_model(dev)
+    model.train()
+    b1, b2 = make_batch(dev, 2, 32, 48, seed=1), make_batch(dev, 2, 32, 48, seed=2)
+    d1 = model(b1["input"])
+    d2 = model(b2["input"])
+    with pytest.raises(RuntimeError, match="ONE training forward"):
+        d1.sum().backward()
+    d2.sum().backward()
+    assert model.logvar_head.weight.grad is None and model.logvar_head.bias.grad is None
+    assert model.disparity_head.weight.grad is not None and model.enc1.block[0].weight.grad is not None
+    # gradient accumulation over several forward/backward pairs is what autograd users do: still fine
+    g1 = model.disparity_head.weight.grad.clone()
+    model(b2["input"]).sum().backward()
+    assert torch.allclose(model.disparity_head.weight.grad, 2 * g1, rtol=1e-3, atol=1e-6)
 
 
 # ------------------------------------------------------------------ fused step
