@@ -26,7 +26,7 @@
 
 namespace sdn {
 
-enum : int { CG_RELU = 1, CG_STATS = 2, CG_BRES = 4, CG_DBG_NOMMA = 64, CG_DBG_NOEPI = 128, CG_DBG_NOLOADA = 256, CG_DBG_NOSTORE = 512, CG_DBG_NOSTATS = 1024 };
+enum : int { CG_RELU = 1, CG_STATS = 2, CG_BRES = 4, CG_BSTATS = 8, CG_DBG_NOMMA = 64, CG_DBG_NOEPI = 128, CG_DBG_NOLOADA = 256, CG_DBG_NOSTORE = 512, CG_DBG_NOSTATS = 1024 };
 
 struct CgSeg {
     int8_t map;  // index into a_maps
@@ -58,7 +58,16 @@ struct alignas(64) ConvGemmParams {
     int b_res_bytes;        // CG_BRES: the whole packed weight matrix lives in shared memory (loaded once per CTA)
     int ups;                // HALO: units (k-blocks) per pipeline stage (1 or 3): fewer producer/MMA handshakes per tile
     const float* bias;      // [n_total] or nullptr; added before ReLU
-    float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS
+    float* stats_partials;  // [gridDim.x][2 * n_total] when CG_STATS / CG_BSTATS
+    // CG_BSTATS (data-gradient kernels): the tile just produced is dA of a conv+BN+ReLU layer; the epilogue also
+    // TMA-loads the matching tile of that layer's pre-BN output y and reduces the two BatchNorm-backward sums
+    //   s1[c] = sum dz,  q[c] = sum dz * (y - mean[c]),   dz = (y*scale[c] + shift[c] > 0) ? dA : 0
+    // into stats_partials, so the separate reduction pass over (y, dA) disappears.
+    CUtensorMap y_map;      // same box / swizzle as d_maps[0], over y
+    const float* bs_scale;  // [n_total] each
+    const float* bs_shift;
+    const float* bs_mean;
+    int ybuf;               // y staging buffers per epilogue group (1 or 2)
     long long* dbg;         // optional: block 0 records clock64() per role / tile / event (timing forensics)
 };
 // Timing forensics (clock64 stamps per role / tile, ablation flags) compile in only with
@@ -155,15 +164,18 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
     const int stage_bytes = ups * unit_bytes;
     uint8_t* b_res = smem + stages * stage_bytes;                 // resident weights (CG_BRES), 1024-aligned
     uint8_t* stg0 = b_res + (bres ? p.b_res_bytes : 0);           // D staging (DBUF buffers), 1024-aligned
-    float* scratch = reinterpret_cast<float*>(stg0 + Cfg::DBUF * Cfg::D_BYTES);
-    uint64_t* bars =
-        reinterpret_cast<uint64_t*>(stg0 + Cfg::DBUF * Cfg::D_BYTES + Cfg::SCRATCH_BYTES + Cfg::ACC_BYTES);
+    const bool bstats = (p.flags & CG_BSTATS) != 0;
+    uint8_t* ystg0 = stg0 + Cfg::DBUF * Cfg::D_BYTES;             // y tiles (CG_BSTATS), 1024-aligned
+    const int ystg_bytes = bstats ? Cfg::EG * p.ybuf * Cfg::D_BYTES : 0;
+    float* scratch = reinterpret_cast<float*>(ystg0 + ystg_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ystg0 + ystg_bytes + Cfg::SCRATCH_BYTES + Cfg::ACC_BYTES);
     uint64_t* full_bar = bars;         // [8]
     uint64_t* empty_bar = bars + 8;    // [8]
     uint64_t* tfull_bar = bars + 16;   // [2]
     uint64_t* tempty_bar = bars + 18;  // [2]
     uint64_t* bres_bar = bars + 20;    // resident-weights arrival
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* ybar_all = bars + 24;    // [EG][2] y-tile arrival (CG_BSTATS)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -180,12 +192,14 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             ptx::mbar_init(&tempty_bar[a], 4);
         }
         ptx::mbar_init(bres_bar, 1);
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(&ybar_all[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.a_maps[i]);
         ptx::prefetch_tmap(&p.b_map);
         for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.d_maps[i]);
+        if (bstats) ptx::prefetch_tmap(&p.y_map);
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -403,6 +417,24 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
         int sbuf = 0;
         int dbg_it = 0;
         const int dmap_div = p.n_per_dmap;   // channels per destination map
+        // CG_BSTATS: y tiles of this group's tiles, fetched `ybuf` tiles ahead by the group's first thread
+        uint8_t* ystg = ystg0 + eg * p.ybuf * Cfg::D_BYTES;
+        uint64_t* ybar = ybar_all + eg * 2;
+        const int ybufs = bstats ? p.ybuf : 1;
+        ptx::TileWalker twy;
+        auto issue_y = [&](int buf) {
+            ptx::mbar_arrive_expect_tx(&ybar[buf], Cfg::D_BYTES);
+            const int c0 = twy.n_tile * BLOCK_N;
+#pragma unroll
+            for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk)
+                ptx::tma_load_4d(ystg + buf * Cfg::D_BYTES + cbk * Cfg::D_BLOCK_BYTES, &p.y_map, &ybar[buf],
+                                 c0 + cbk * Cfg::DCH, twy.tx * p.TW, twy.ty * p.TH, twy.tn * p.TN);
+        };
+        if (bstats && te == 0) {
+            twy.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
+            for (int b = 0; b < ybufs && twy.valid(); ++b, twy.next()) issue_y(b);
+        }
+        int yk = 0;   // tiles this group has processed
         ptx::TileWalker tw;
         for (tw.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid();
              tw.next()) {
@@ -423,6 +455,8 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             }
             ptx::named_bar_sync(1 + eg, 128);
             if (dbg_lead) SDN_DBG(2, dbg_tile, 1);
+            // every thread of the group is past the previous tile's statistics pass: its y buffer is free
+            if (bstats && te == 0 && yk >= 1 && twy.valid()) { issue_y((yk - 1) % ybufs); twy.next(); }
 
             ptx::mbar_wait(&tfull_bar[a], aph);
             ptx::tc_fence_after();
@@ -497,7 +531,44 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                 ptx::tma_store_commit();
             }
             if (dbg_lead) SDN_DBG(2, dbg_tile, 6);
-            if (!Cfg::REGSTATS && do_stats) {
+            if (bstats) {
+                // BatchNorm-backward sums of the layer whose output gradient this tile is (see ConvGemmParams):
+                // each thread owns one 32-bit word column (2 channels) of one row group; dA from the staged bf16
+                // values (what the apply pass will read back), y from the TMA-loaded tile at the same offsets.
+                const int yb = yk % ybufs;
+                ptx::mbar_wait(&ybar[yb], uint32_t(yk / ybufs) & 1u);
+#pragma unroll
+                for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk) {
+                    const int ch0 = n_tile * BLOCK_N + cbk * Cfg::DCH + 2 * st_w;
+                    const float sc0 = __ldg(p.bs_scale + ch0), sc1 = __ldg(p.bs_scale + ch0 + 1);
+                    const float sh0 = __ldg(p.bs_shift + ch0), sh1 = __ldg(p.bs_shift + ch0 + 1);
+                    const float mu0 = __ldg(p.bs_mean + ch0), mu1 = __ldg(p.bs_mean + ch0 + 1);
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    const uint8_t* blk = stg + cbk * Cfg::D_BLOCK_BYTES;
+                    const uint8_t* yblk = ystg + yb * Cfg::D_BYTES + cbk * Cfg::D_BLOCK_BYTES;
+#pragma unroll 8
+                    for (int rr = 0; rr < STAT_ROWS; ++rr) {
+                        const int row = st_rg * STAT_ROWS + rr;
+                        const int j = st_w >> 2;
+                        const int sw = (Cfg::SWD == 128) ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3));
+                        const int off = row * Cfg::SWD + (sw << 4) + ((st_w & 3) << 2);
+                        const uint32_t u = *reinterpret_cast<const uint32_t*>(blk + off);
+                        const uint32_t yv = *reinterpret_cast<const uint32_t*>(yblk + off);
+                        const float g_lo = __uint_as_float(u << 16), g_hi = __uint_as_float(u & 0xFFFF0000u);
+                        const float y_lo = __uint_as_float(yv << 16), y_hi = __uint_as_float(yv & 0xFFFF0000u);
+                        const float d_lo = fmaf(y_lo, sc0, sh0) > 0.f ? g_lo : 0.f;
+                        const float d_hi = fmaf(y_hi, sc1, sh1) > 0.f ? g_hi : 0.f;
+                        s0 += d_lo; q0 = fmaf(d_lo, y_lo - mu0, q0);
+                        s1 += d_hi; q1 = fmaf(d_hi, y_hi - mu1, q1);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < Cfg::NT; ++nt)
+                        if (nt == n_tile || Cfg::NT == 1) {
+                            st_acc[nt][cbk][0] += s0; st_acc[nt][cbk][1] += s1;
+                            st_acc[nt][cbk][2] += q0; st_acc[nt][cbk][3] += q1;
+                        }
+                }
+            } else if (!Cfg::REGSTATS && do_stats) {
                 // per-channel sum / sum of squares of the bf16 values just staged (== what the
                 // next kernel reads back).  Each thread owns one 32-bit word column (2 channels)
                 // of one row group and keeps its partials in REGISTERS across tiles; the
@@ -528,6 +599,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             }
             if (dbg_lead) SDN_DBG(2, dbg_tile, 5);
             sbuf = (Cfg::DBUF == 2) ? (sbuf ^ 1) : 0;
+            ++yk;
             if (EG == 2) {
                 aph ^= 1;
             } else {
@@ -535,7 +607,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                 if (a == 0) aph ^= 1;
             }
         }
-        if (Cfg::REGSTATS && do_stats) {
+        if (Cfg::REGSTATS && do_stats && !bstats) {
             // one reduction per kernel: 32 rows by warp shuffle, the group's 4 warps through scratch
             float* dst = p.stats_partials + size_t(blockIdx.x * EG + eg) * 2 * p.n_total;
             scratch += eg * (Cfg::SCRATCH_BYTES / 4 / EG);
@@ -556,7 +628,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                 const int kind = o / BLOCK_N, c = o % BLOCK_N;
                 if (c < p.n_total) dst[kind * p.n_total + c] = v;
             }
-        } else if (do_stats) {
+        } else if (do_stats || bstats) {
             // one cross-row-group reduction per kernel: scratch[rg][channel] -> per-CTA partials
             float* dst = p.stats_partials + size_t(blockIdx.x * EG + eg) * 2 * p.n_total;
             scratch += eg * (Cfg::SCRATCH_BYTES / 4 / EG);

@@ -524,9 +524,11 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
 }
 
 // partials -> c1, c2 and the affine parameter gradients (dgamma = sum(dz*xhat), dbeta = sum(dz)).
+// rstd_scale (nullable): the second partial column holds sum(dz * (y - mean)) instead of sum(dz * xhat) (the
+// fused conv-epilogue reduction, CG_BSTATS): multiply by rstd[c] here.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate) {
+                                       float* __restrict__ dbeta, int accumulate, const float* __restrict__ rstd_scale) {
     SDN_PDL_ENTRY();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
     const int lane = threadIdx.x & 31;
@@ -541,6 +543,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     if (lane != 0) return;
+    if (rstd_scale != nullptr) s2 *= (double)rstd_scale[c];
     c1[c] = (float)(s1 / count);
     c2[c] = (float)(s2 / count);
     if (dgamma != nullptr) {

@@ -184,6 +184,10 @@ struct ConvL {  // conv3x3 + BatchNorm + ReLU
     GemmOp fprop, fprop_eval, dgrad;   // fprop_eval: BN folded, epilogue = +shift, ReLU, writes `a` directly
     WgradOp wgrad;
     bool has_dgrad = true;
+    // the kernel that writes `ga` (the next layer's dgrad, or a ConvTranspose2d dgrad) also reduced this layer's
+    // BatchNorm-backward sums (CG_BSTATS): bn_backward skips its reduction pass and finalizes from these partials
+    bool bwd_stats_fused = false;
+    int bwd_stats_parts = 0;
 };
 struct UpL {  // ConvTranspose2d(k=2, s=2)
     int cin = 0, cout = 0, lvl_in = 0;
@@ -487,10 +491,15 @@ static int first_rows() {
     return v;
 }
 
+// BatchNorm-backward statistics fused into a data-gradient epilogue (CG_BSTATS): the layer whose dA the op writes
+struct BStatSpec {
+    const Act* y;
+    const float *scale, *shift, *mean;
+};
 static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
                       const std::vector<SegSpec>& segs_in, const bf16* bmat, int n_total,
                       const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
-                      float* stats_partials, bool conv3x3 = false, int dx_taps = 3) {
+                      float* stats_partials, bool conv3x3 = false, int dx_taps = 3, const BStatSpec* bs = nullptr) {
     static const int g_halo_max_n = env_int("SDN_HALO_MAXN", 128);   // largest BLOCK_N that uses the row-halo kernel (0 disables)
     std::vector<SegSpec> segs = segs_in;
     if (aviews.empty() || aviews.size() > 4 || dviews.empty() || dviews.size() > 4 || segs.size() > CG_MAX_SEGS)
@@ -517,7 +526,10 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     }
     if (op.swa == 64 && bn > 64) bn = 64;
     const int W = dviews[0].W, H = dviews[0].H;
-    if (!(flags & CG_STATS)) {
+    static const int bstats_on = env_int("SDN_BSTATS", 1);
+    if (bs != nullptr && !(bstats_on && dviews.size() == 1 && n_per_dmap == n_total && bn == n_total && bn <= 128 && !op.swd64))
+        bs = nullptr;   // wide / split tiles keep the separate reduction pass (levels 4-5: few bytes)
+    if (!(flags & CG_STATS) && bs == nullptr) {
         // latency regime (few pixels): narrower N tiles spread the K loop over more CTAs
         const long long m_est = ((long long)W * H * B + 127) / 128;
         while (bn > 32 && m_est * (n_total / bn) < c->num_sms / 2) {
@@ -598,6 +610,21 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         SDN_OK(encode4(&p.d_maps[i], v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, dch, t.TW, t.TH, t.TN, swd));
     }
     for (size_t i = dviews.size(); i < 4; ++i) p.d_maps[i] = p.d_maps[0];
+    int ybytes = 0;
+    if (bs != nullptr) {
+        const SrcView v = full_view(*bs->y);
+        if (v.C != n_total || v.W != W || v.H != H) return fail("build_gemm: BatchNorm-backward statistics need y of the destination's shape");
+        SDN_OK(encode4(&p.y_map, v.base, v.C, v.W, v.H, B, v.sW, v.sH, v.sN, dch, t.TW, t.TH, t.TN, swd));
+        flags |= CG_BSTATS;
+        stats_partials = c->stats_partials;
+        p.bs_scale = bs->scale; p.bs_shift = bs->shift; p.bs_mean = bs->mean;
+        // small tiles are epilogue-bound: fetch y two tiles ahead; wide tiles hide one fetch behind their main loop
+        p.ybuf = bn <= 64 ? 2 : 1;
+        ybytes = (bn <= 64 ? 2 : 1) * p.ybuf * 128 * bn * 2;
+    } else {
+        p.y_map = p.d_maps[0];
+        p.ybuf = 1;
+    }
     p.n_tiles = n_total / bn;
     p.n_per_dmap = n_per_dmap;
     p.n_total = n_total;
@@ -608,7 +635,12 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     int stages = 8;
     if (op.halo == 2) {
         const int b_total = kblocks * 9 * bn * op.swa;
-        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);
+        int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;
+        if (bs != nullptr && p.ybuf == 2 && (220 * 1024 - fixed - b_total) / p.a_stage_bytes < 3) {
+            p.ybuf = 1;            // big resident weights (64 -> 64): keep three pipeline stages instead
+            fixed -= ybytes / 2;
+            ybytes /= 2;
+        }
         p.flags |= CG_BRES;
         p.b_res_bytes = b_total;
         const int budget = 220 * 1024 - fixed - b_total;
@@ -622,7 +654,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
         const int b_total = kblocks * 3 * bn * op.swa;
         static const int ups_on = env_int("SDN_UPS", 3);
-        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes);   // staging, scratch, barriers
+        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
         if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
         const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn * op.swa);
@@ -635,8 +667,8 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
             while (stages > 2 && CgCfg<128, 128, 64>::smem_bytes(stages) > 220 * 1024) --stages;
             op.smem = CgCfg<128, 128, 64>::smem_bytes(stages);
         } else {
-            while (stages > 2 && cg_smem(op.swa, bn, stages) > 220 * 1024) --stages;
-            op.smem = cg_smem(op.swa, bn, stages);
+            while (stages > 2 && cg_smem(op.swa, bn, stages) + ybytes > 220 * 1024) --stages;
+            op.smem = cg_smem(op.swa, bn, stages) + ybytes;
         }
     }
     p.stages = stages;
@@ -941,7 +973,17 @@ static int prepare_batch(sdn_ctx* c, int B) {
             } else {
                 dv.push_back(full_view(c->conv[i - 1].gp));
             }
-            SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr, true));
+            // i odd: the destination is dA of conv[i-1] (never a pooled layer): its BatchNorm-backward sums come
+            // out of this kernel's epilogue
+            BStatSpec bspec{};
+            ConvL* target = (i % 2 == 1) ? &c->conv[i - 1] : nullptr;
+            if (target != nullptr) bspec = BStatSpec{&target->y, target->scale, target->shift, target->mean};
+            SDN_OK(build_gemm(c, L.dgrad, B, {full_view(L.dy)}, dsegs, L.wd, L.cin, dv, n_per, nullptr, 0, nullptr, true, 3,
+                              target ? &bspec : nullptr));
+            if (target != nullptr) {
+                target->bwd_stats_fused = (L.dgrad.p.flags & CG_BSTATS) != 0;
+                target->bwd_stats_parts = L.dgrad.grid * (L.dgrad.block_n <= 64 ? 2 : 1);
+            }
             if (L.nsrc == 2) {
                 // the first destination is the up-conv output gradient: its per-channel column sums are the
                 // ConvTranspose2d bias gradient, and the epilogue can produce them like BatchNorm statistics
@@ -966,8 +1008,12 @@ static int prepare_batch(sdn_ctx* c, int B) {
         SDN_OK(build_gemm(c, U.fprop, B, {full_view(*U.src)}, {{0, 0, 0}}, U.wf, 4 * U.cout, quads_u, U.cout, U.bias4,
                           0, nullptr));
         std::vector<SegSpec> qsegs = {{0, 0, 0}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}};
-        SDN_OK(build_gemm(c, U.dgrad, B, quads_gu, qsegs, U.wd, U.cin, {full_view(c->conv[U.src_layer].ga)}, U.cin,
-                          nullptr, 0, nullptr));
+        ConvL& T = c->conv[U.src_layer];     // bottleneck.3 / dec4.3 / dec3.3 / dec2.3: not pooled
+        const BStatSpec bspec{&T.y, T.scale, T.shift, T.mean};
+        SDN_OK(build_gemm(c, U.dgrad, B, quads_gu, qsegs, U.wd, U.cin, {full_view(T.ga)}, U.cin, nullptr, 0, nullptr, false, 3,
+                          &bspec));
+        T.bwd_stats_fused = (U.dgrad.p.flags & CG_BSTATS) != 0;
+        T.bwd_stats_parts = U.dgrad.grid * (U.dgrad.block_n <= 64 ? 2 : 1);
         SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
     }
     c->B = B;
@@ -1161,18 +1207,25 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     const double count = (double)B * H * W;
     const bool pool = L.pooled_out;
     const long long items = pool ? (long long)B * (H / 2) * (W / 2) * (C / 8) : (long long)B * H * W * (C / 8);
-    int grid = pool ? occ_grid(c, bn_bwd_reduce_kernel<true>, items, 256) : occ_grid(c, bn_bwd_reduce_kernel<false>, items, 256);
-    grid = std::min(grid, BWD_BLOCKS);
-    if (pool)
-        launch_k(bn_bwd_reduce_kernel<true>, grid, 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd,
-                                                         c->bwd_partials, B, H, W, C);
-    else
-        launch_k(bn_bwd_reduce_kernel<false>, grid, 256, 0, st, L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
-                                                          c->bwd_partials, B, H, W, C);
-    ++c->launches;
-    launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->bwd_partials, grid, C, count, L.c1, L.c2,
-                                                            c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate);
-    ++c->launches;
+    if (L.bwd_stats_fused) {
+        // the kernel that produced `ga` already reduced sum(dz) and sum(dz * (y - mean)) per CTA (CG_BSTATS)
+        launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->stats_partials, L.bwd_stats_parts, C, count,
+                 L.c1, L.c2, c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)L.rstd);
+        ++c->launches;
+    } else {
+        int grid = pool ? occ_grid(c, bn_bwd_reduce_kernel<true>, items, 256) : occ_grid(c, bn_bwd_reduce_kernel<false>, items, 256);
+        grid = std::min(grid, BWD_BLOCKS);
+        if (pool)
+            launch_k(bn_bwd_reduce_kernel<true>, grid, 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd,
+                                                             c->bwd_partials, B, H, W, C);
+        else
+            launch_k(bn_bwd_reduce_kernel<false>, grid, 256, 0, st, L.y.p, L.ga.p, nullptr, nullptr, L.scale, L.shift, L.mean, L.rstd,
+                                                              c->bwd_partials, B, H, W, C);
+        ++c->launches;
+        launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->bwd_partials, grid, C, count, L.c1, L.c2,
+                                                                c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)nullptr);
+        ++c->launches;
+    }
     if (pool)
         launch_k(bn_bwd_apply_kernel<true>, occ_grid(c, bn_bwd_apply_kernel<true>, items, 256), 256, 0, st, L.y.p, L.ga.p, L.gp.p, L.amax, L.scale, L.shift, L.mean, L.rstd, L.c1,
                                                          L.c2, L.dy.p, B, H, W, C);
@@ -1189,7 +1242,8 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
     const double px = (double)B * L.y.H * L.y.W;
     {
         // reduce: y + g (+ gp/4); apply: y + g (+ gp/4) + dy
-        ProfScope ps(c, st, "bn_bwd", i, 0.0, px * L.cout * 2 * (L.pooled_out ? 5.5 : 5.0));
+        // reduce: y + g (+ gp/4) [skipped when the producer of g reduced the sums]; apply: y + g (+ gp/4) + dy
+        ProfScope ps(c, st, "bn_bwd", i, 0.0, px * L.cout * 2 * (L.pooled_out ? 5.5 : (L.bwd_stats_fused ? 3.0 : 5.0)));
         SDN_OK(bn_backward(c, L, B, st));
     }
     {
@@ -1213,8 +1267,9 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
             ProfScope ps(c, ws, "conv_wgrad", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
             SDN_OK(launch_wg(c, L.wgrad, ws));
         }
+        const bool dgrad_reads_y = L.has_dgrad && (L.dgrad.p.flags & CG_BSTATS) != 0;   // + the target layer's y tile
         ProfScope ps2(c, st, L.has_dgrad ? "conv_dgrad" : "grad_unpack", i, L.has_dgrad ? 2.0 * px * L.cout * 9 * L.cin : 0.0,
-                      L.has_dgrad ? px * (L.cin + L.cout) * 2 : 0.0);
+                      L.has_dgrad ? px * (L.cin * (dgrad_reads_y ? 2 : 1) + L.cout) * 2 : 0.0);
         if (c->grads[L.p_w] != nullptr) {
             const int n = 9 * L.cin * L.cout;
             launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, L.wg, c->grads[L.p_w], L.first ? (first_rows() ? 4 : 2) : 0, L.cout, L.cin,
@@ -1259,7 +1314,8 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
         ProfScope ps(c, ws, "convT_wgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
         SDN_OK(launch_wg(c, U.wgrad, ws));
     }
-    ProfScope ps2(c, st, "convT_dgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout, pxin * (U.cin + 4 * U.cout) * 2);
+    ProfScope ps2(c, st, "convT_dgrad", 100 + k, 2.0 * pxin * U.cin * 4 * U.cout,
+                  pxin * (U.cin * ((U.dgrad.p.flags & CG_BSTATS) ? 2 : 1) + 4 * U.cout) * 2);
     if (c->grads[U.p_w] != nullptr) {
         const int n = 4 * U.cin * U.cout;
         launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);

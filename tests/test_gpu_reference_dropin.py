@@ -124,13 +124,17 @@ def test_reference_run_epoch_train_and_val_on_dropin(dev, ref):
           f"torch-autocast mean {ymean:.4f} min {yard[yworst]:.4f} ({yworst})")
     assert mean_cos >= ymean - 0.05 and cosines[worst] >= min(0.5, yard[yworst] - 0.1), (mean_cos, ymean, worst)
     # BatchNorm buffers (part of the checkpoint): running statistics after 4 train steps
-    so, sr = ours.state_dict(), ref_model.state_dict()
+    so, sr, sa = ours.state_dict(), ref_model.state_dict(), ac_model.state_dict()
+    worst_buf = (0.0, 0.0, "")
     for k in sr:
         if k.endswith("num_batches_tracked"):
             assert int(so[k]) == int(sr[k]) == 4, k
         elif "running_" in k:
             rel = float((so[k] - sr[k]).norm() / sr[k].norm().clamp(min=1e-30))
-            assert rel <= 3e-2, (k, rel)
+            yrel = float((sa[k] - sr[k]).norm() / sr[k].norm().clamp(min=1e-30))
+            worst_buf = max(worst_buf, (rel, yrel, k))
+            assert rel <= max(3e-2, 1.5 * yrel), (k, rel, yrel)      # (weights have separated by step 4)
+    print(f"worst BatchNorm buffer after 4 steps: ours {worst_buf[0]:.2e} torch-autocast {worst_buf[1]:.2e} ({worst_buf[2]})")
 
     # validation epoch at IDENTICAL weights: run_epoch(optimizer=None) (train.py:618)
     ours.load_state_dict(ref_model.state_dict())
