@@ -122,7 +122,7 @@ struct CgCfg {
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
     static constexpr int DBUF = BLOCK_N <= 64 ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
-    static constexpr int NT = BLOCK_N == 256 ? 2 : 1;    // N tiles a stats layer can have (Cout = 512)
+    static constexpr int NT = BLOCK_N >= 128 ? 512 / BLOCK_N : 1;    // N tiles a stats layer can have (Cout <= 512)
     static constexpr int smem_bytes(int stages) {
         return 1024 + stages * STAGE_BYTES + DBUF * D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
     }

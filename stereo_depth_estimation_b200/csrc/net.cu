@@ -239,7 +239,7 @@ struct sdn_ctx {
     // BatchNorm backward of the following layer (dgrad -> BN backward is the critical path; a wgrad and a
     // dgrad cannot share an SM, a wgrad and the shared-memory-free BN kernels can).
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
     bool side_dirty = false;
     // Data parallelism (sdn_comm_init): one NCCL communicator per context; gradient buckets are all-reduced on
     // `comm_stream`, forked from the caller's stream after each backward stage and joined at the end of the step.
@@ -526,6 +526,18 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     }
     if (op.swa == 64 && bn > 64) bn = 64;
     const int W = dviews[0].W, H = dviews[0].H;
+    if (bn == 256 && n_per_dmap % 128 == 0) {
+        // Wave quantisation on the small levels: a persistent grid of num_sms CTAs runs ceil(jobs / num_sms)
+        // rounds.  Halving the N tile doubles the jobs at half the cost each (N = 128 MMAs keep the pipe as busy
+        // as N = 256 ones: 67 vs 131 cycles per K = 16 step) and can save most of a nearly-empty last round:
+        // 32 pairs at 15x20: 150 jobs = 2 rounds -> 300 half-jobs = 1.5; at 30x40: 3 -> 2.5.  The A tile is then
+        // fetched once per N tile (L2-resident at these sizes), hence the 5 % bar.
+        static const int nsplit_on = env_int("SDN_NSPLIT", 1);
+        const long long m_jobs = ((long long)W * H * B + 127) / 128;
+        const long long r256 = (m_jobs * (n_total / 256) + c->num_sms - 1) / c->num_sms * 2;
+        const long long r128 = (m_jobs * (n_total / 128) + c->num_sms - 1) / c->num_sms;
+        if (nsplit_on && r128 * 1.03 < 0.95 * r256) bn = 128;
+    }
     static const int bstats_on = env_int("SDN_BSTATS", 1);
     if (bs != nullptr && !(bstats_on && dviews.size() == 1 && n_per_dmap == n_total && bn == n_total && bn <= 128 && !op.swd64))
         bs = nullptr;   // wide / split tiles keep the separate reduction pass (levels 4-5: few bytes)
@@ -631,7 +643,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.flags = flags;
     p.bias = bias;
     p.stats_partials = stats_partials;
-    if ((flags & CG_STATS) && n_total > 512) return fail("build_gemm: stats need n_total <= 512");
+    if ((flags & CG_STATS) && (n_total > 512 || (p.n_tiles > 1 && bn < 128))) return fail("build_gemm: stats need n_total <= 512 and N tiles of >= 128 channels");
     int stages = 8;
     if (op.halo == 2) {
         const int b_total = kblocks * 9 * bn * op.swa;
@@ -1050,8 +1062,10 @@ static int zero_fill(sdn_ctx* c, void* p, size_t bytes, cudaStream_t st) {
 }
 
 // bf16 operand cache <- fp32 parameters: one launch for every layer
-static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
-    ProfScope ps(c, st, "pack_weights", 0, 0.0, 7763938.0 * (4 + 2) * (training ? 2 : 1));
+// part 0: the first PACK_SHALLOW conv layers (needed at once), part 1: everything else, part 2: all
+static const int PACK_SHALLOW = 4;
+static int pack_params(sdn_ctx* c, bool training, cudaStream_t st, int part = 2) {
+    ProfScope ps(c, st, "pack_weights", 0, 0.0, part == 0 ? 0.0 : 7763938.0 * (4 + 2) * (training ? 2 : 1));
     const bool fold = !training;   // eval: BatchNorm scale folded into the forward weights
     PackTable t;
     t.n = 0;
@@ -1060,9 +1074,10 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
         PackEntry& e = t.e[t.n++];
         e.w = w; e.dst = dst; e.oscale = oscale; e.mode = mode; e.Co = Co; e.Ci = Ci; e.Kpad = Kpad;
         e.start = t.total;
-        t.total += count;
+        t.total += (count + 7) & ~7;     // pack_all_kernel works in runs of 8 elements
     };
     for (int i = 0; i < 18; ++i) {
+        if ((part == 0 && i >= PACK_SHALLOW) || (part == 1 && i < PACK_SHALLOW)) continue;
         ConvL& L = c->conv[i];
         const float* w = c->params[L.p_w];
         if (L.first && first_rows()) {
@@ -1076,14 +1091,14 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st) {
             if (training) add(w, L.wd, nullptr, dmode[L.dgrad.halo], L.cout, L.cin, L.dgrad.swa / 2, n);
         }
     }
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4 && part != 0; ++k) {
         UpL& U = c->up[k];
         const int n = 4 * U.cin * U.cout;
         add(c->params[U.p_w], U.wf, nullptr, 3, U.cout, U.cin, 0, n);
         if (training) add(c->params[U.p_w], U.wd, nullptr, 4, U.cout, U.cin, 0, n);
         add(c->params[U.p_b], U.bias4, nullptr, 7, U.cout, 0, 0, 4 * U.cout);
     }
-    launch_k(pack_all_kernel, c->num_sms * 4, 256, 0, st, t);
+    launch_k(pack_all_kernel, part == 0 ? c->num_sms : c->num_sms * 4, 256, 0, st, t);
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1121,7 +1136,23 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             ++c->launches;
         }
     }
-    if (dirty) SDN_OK(pack_params(c, training != 0, st));
+    // The deep layers hold 99 % of the packed bytes and are not needed before enc3: their packing runs on the side
+    // stream next to the first-layer taps kernel and the level-1/2 convs (0.09 ms per step whatever the batch,
+    // i.e. 1.5 % of a 32-pair step), the main stream joins right before conv 4.
+    static const int pack_overlap = env_int("SDN_PACK_OVERLAP", 0);   // measured: the low-priority side stream delays the join (6.11 -> 6.17 ms at 32 pairs)
+    bool pack_pending = false;
+    if (dirty) {
+        if (pack_overlap && training && c->side != nullptr && !c->prof) {
+            CUDA_OK(cudaEventRecord(c->ev_fork, st));
+            CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            SDN_OK(pack_params(c, true, c->side, 1));
+            CUDA_OK(cudaEventRecord(c->ev_pack, c->side));
+            SDN_OK(pack_params(c, true, st, 0));
+            pack_pending = true;
+        } else {
+            SDN_OK(pack_params(c, training != 0, st));
+        }
+    }
     const int H = c->H, W = c->W;
     {
         const double px = (double)B * H * W;
@@ -1137,6 +1168,10 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
     CUDA_OK(cudaGetLastError());
     for (int i = 0; i < 18; ++i) {
         ConvL& L = c->conv[i];
+        if (pack_pending && i == PACK_SHALLOW) {
+            CUDA_OK(cudaStreamWaitEvent(st, c->ev_pack, 0));
+            pack_pending = false;
+        }
         if (i >= 10 && i % 2 == 0) {
             UpL& U = c->up[(i - 10) / 2];
             const double px = (double)B * U.src->H * U.src->W;
@@ -1506,6 +1541,7 @@ int sdn_create(sdn_ctx** out, int device, int max_batch, int H, int W, unsigned 
         CUDA_OK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
     }
     *out = c;
     return 0;
@@ -1518,6 +1554,7 @@ int sdn_destroy(sdn_ctx* c) {
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ws) cudaFree(c->ws);
     delete c;
     return 0;
