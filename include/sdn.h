@@ -158,6 +158,28 @@ int sdn_preprocess(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, cons
                    int Ws, const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
                    unsigned long long* valid_count, unsigned flags, void* stream);
 
+/* The same sample on a CACHE HIT (dataset.py:86-106 load_cached_sample, then 302-311): the npz read-through
+ * cache holds uint8 HWC views [B,H,W,3] and a FLOAT16 disparity [B,H,W] already at the context's H x W, so
+ * there is no resize and no disparity rescale: views = u8 / 255, target = (float)f16, then the same
+ * augmentation / cat / valid_mask / count as sdn_preprocess (aug, flags: as there). */
+int sdn_preprocess_cached(sdn_ctx* ctx, const uint8_t* left, const uint8_t* right, const uint16_t* disparity_f16, int B,
+                          const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
+                          unsigned long long* valid_count, unsigned flags, void* stream);
+
+/* Live viewer, per frame (src/live_camera/depth_live_dl.py).
+ * sdn_live_preprocess = preprocess_rgb(view_l), preprocess_rgb(view_r), cat (:225-229, 516-520): two BGR uint8
+ * frames [Hs,Ws,3] on the device -> the model input [1,6,H,W] float32 (H x W = the context's); the uint8
+ * INTER_LINEAR resize reproduces cv2.resize's fixed-point arithmetic bit-exactly.
+ * sdn_live_postprocess (:531-538, 371-381): optional EMA of the disparity (ema_state: device float[n], kept by
+ * the caller between frames; ema_has_state == 0 on the first frame; ema_alpha <= 0 or NULL state = off),
+ * depth = focal_px * baseline_m / d where d is finite and > 1e-6 (NaN elsewhere), confidence =
+ * exp(-0.5 * logvar).  disp_out / depth_out / conf_out are optional (NULL skips). */
+int sdn_live_preprocess(sdn_ctx* ctx, const uint8_t* frame_left_bgr, const uint8_t* frame_right_bgr, int Hs, int Ws,
+                        float* input, void* stream);
+int sdn_live_postprocess(sdn_ctx* ctx, const float* disp, const float* logvar, int64_t n_pixels, float* ema_state,
+                         int ema_has_state, double ema_alpha, double focal_px, double baseline_m, float* disp_out,
+                         float* depth_out, float* conf_out, void* stream);
+
 /* Test / debug access to the NHWC bf16 activations of the last forward:
  * which = conv layer index 0..17 (100..103: the ConvTranspose2d outputs); kind 0 = pre-BN conv output, 1 = post
  * BN+ReLU, 2 = gradient w.r.t. the pre-BN output (after backward), 3 = gradient w.r.t. the post-ReLU output,

@@ -4,5 +4,6 @@ sdfgeoff/stereo_depth_estimation.  Host side in Python over a C-ABI CUDA library
 from .model import ConvBlock, StereoUNet, load_state_dict_compat  # noqa: F401
 
 from .pipeline import SourcePrefetcher  # noqa: F401
+from .live import LivePipeline  # noqa: F401
 
-__all__ = ["StereoUNet", "ConvBlock", "load_state_dict_compat", "SourcePrefetcher"]
+__all__ = ["StereoUNet", "ConvBlock", "load_state_dict_compat", "SourcePrefetcher", "LivePipeline"]

@@ -46,6 +46,9 @@ EXPORTS = (
     "sdn_comm_world",
     "sdn_comm_allreduce",
     "sdn_preprocess",
+    "sdn_preprocess_cached",
+    "sdn_live_preprocess",
+    "sdn_live_postprocess",
     "sdn_debug_read",
     "sdn_adamw_step",
     "sdn_debug_trace",
@@ -129,6 +132,14 @@ def load() -> ctypes.CDLL:
     lib.sdn_preprocess.restype = c_int
     lib.sdn_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_uint, c_void_p]
+    lib.sdn_preprocess_cached.restype = c_int
+    lib.sdn_preprocess_cached.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_uint, c_void_p]
+    lib.sdn_live_preprocess.restype = c_int
+    lib.sdn_live_preprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.sdn_live_postprocess.restype = c_int
+    lib.sdn_live_postprocess.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sdn_adamw_step.restype = c_int
     lib.sdn_adamw_step.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_int64), c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,

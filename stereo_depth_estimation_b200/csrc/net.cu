@@ -25,6 +25,7 @@
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
 #include "preprocess.cuh"
+#include "live.cuh"
 #include "wgrad_gemm.cuh"
 #include "wgrad_tr.cuh"
 
@@ -1838,6 +1839,80 @@ int sdn_preprocess(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const 
                                 target + (size_t)b0 * plane, mask + (size_t)b0 * plane, valid_count, flags,
                                 c->gray_part + (size_t)2 * b0 * parts, c->blur_tmp + (size_t)2 * b0 * 3 * plane, st));
     }
+    return 0;
+}
+
+// FoundationStereoDataset.__getitem__ on a cache hit (dataset.py:86-106, 272-311): see live.cuh
+int sdn_preprocess_cached(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint16_t* disparity_f16, int B,
+                          const sdn_aug_params* aug_dev, float* input, float* target, uint8_t* mask,
+                          unsigned long long* valid_count, unsigned flags, void* stream) {
+    if (c == nullptr || left == nullptr || right == nullptr || disparity_f16 == nullptr || input == nullptr ||
+        target == nullptr || mask == nullptr)
+        return fail("sdn_preprocess_cached: NULL argument");
+    if (B < 1 || B > c->maxB) return fail("sdn_preprocess_cached: batch %d outside [1, %d]", B, c->maxB);
+    cudaStream_t st = (cudaStream_t)stream;
+    SDN_ENTER(c);
+    c->pdl = t_pdl = (long long)B * c->H * c->W <= 48LL * 240 * 320 ? 1 : 0;
+    if (valid_count != nullptr) SDN_OK(zero_fill(c, valid_count, sizeof(unsigned long long), st));
+    const AugParams* aug = reinterpret_cast<const AugParams*>(aug_dev);
+    if (aug != nullptr && (flags & SDN_PREPROCESS_AUG_HOST)) {
+        const int words = 2 * B * (int)(sizeof(AugParams) / 4);
+        launch_k(copy_f32_kernel, (words + 255) / 256, 256, 0, st, reinterpret_cast<const float*>(aug_dev), c->aug_stage, words, 0);
+        ++c->launches;
+        aug = reinterpret_cast<const AugParams*>(c->aug_stage);
+    }
+    const int H = c->H, W = c->W;
+    const int parts = ((W + 127) / 128) * ((H + PRE_ROWS - 1) / PRE_ROWS);
+    {
+        // 2 x u8 HWC + f16 read; fp32 input / target + u8 mask written
+        ProfScope ps(c, st, "pre_cached", 0, 0.0, (double)B * H * W * (6 + 2 + 6 * 4 + 4 + 1));
+        launch_k(cached_assemble_kernel, dim3(parts, B), 128, 0, st, left, right, reinterpret_cast<const __half*>(disparity_f16), B, H,
+                 W, input, target, mask, valid_count, aug, aug ? c->gray_part : nullptr, parts);
+        ++c->launches;
+    }
+    if (aug != nullptr) {
+        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
+        launch_k(augment_point_kernel, dim3((H * W + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug, c->gray_part, parts, c->blur_tmp);
+        ++c->launches;
+        launch_k(blur_noise_kernel<5>, dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st, input, B, H, W, aug, c->blur_tmp);
+        ++c->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// preprocess_rgb x 2 + cat (live_camera/depth_live_dl.py:225-229, 516-520): see live.cuh
+int sdn_live_preprocess(sdn_ctx* c, const uint8_t* frame_left_bgr, const uint8_t* frame_right_bgr, int Hs, int Ws,
+                        float* input, void* stream) {
+    if (c == nullptr || frame_left_bgr == nullptr || frame_right_bgr == nullptr || input == nullptr)
+        return fail("sdn_live_preprocess: NULL argument");
+    if (Hs < 1 || Ws < 1) return fail("sdn_live_preprocess: bad frame size %dx%d", Hs, Ws);
+    SDN_ENTER(c);
+    const int H = c->H, W = c->W;
+    // resize.cpp: inv_scale = dsize / ssize; scale = 1. / inv_scale (both double)
+    const double scale_x = 1.0 / ((double)W / (double)Ws), scale_y = 1.0 / ((double)H / (double)Hs);
+    ProfScope ps(c, (cudaStream_t)stream, "live_pre", 0, 0.0, 2.0 * ((double)Hs * Ws * 3 + (double)H * W * 12));
+    launch_k(live_preprocess_kernel, dim3((W + 127) / 128, H, 2), 128, 0, (cudaStream_t)stream, frame_left_bgr, frame_right_bgr, Hs,
+             Ws, H, W, scale_x, scale_y, input);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// EMA (depth_live_dl.py:531-538), disparity_to_depth (:371-377), confidence_from_logvar (:380-381): see live.cuh
+int sdn_live_postprocess(sdn_ctx* c, const float* disp, const float* logvar, int64_t n_pixels, float* ema_state,
+                         int ema_has_state, double ema_alpha, double focal_px, double baseline_m, float* disp_out,
+                         float* depth_out, float* conf_out, void* stream) {
+    if (c == nullptr || disp == nullptr || n_pixels < 1) return fail("sdn_live_postprocess: bad argument");
+    if (conf_out != nullptr && logvar == nullptr) return fail("sdn_live_postprocess: confidence needs logvar");
+    SDN_ENTER(c);
+    const int ema_mode = (ema_state != nullptr && ema_alpha > 0.0) ? (ema_has_state ? 2 : 1) : 0;
+    ProfScope ps(c, (cudaStream_t)stream, "live_post", 0, 0.0, (double)n_pixels * 4 * 6);
+    launch_k(live_postprocess_kernel, occ_grid(c, live_postprocess_kernel, n_pixels, 256), 256, 0, (cudaStream_t)stream, disp, logvar,
+             (long long)n_pixels, ema_state, ema_mode, (float)ema_alpha, (float)(1.0 - ema_alpha),
+             (float)(focal_px * baseline_m), disp_out, depth_out, conf_out);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -163,6 +163,33 @@ class DevicePreprocessor:
     def launch_count(self) -> int:
         return int(_lib.load().sdn_launch_count(self.ctx))
 
+    def _stage_aug(self, aug, b: int):
+        """(device-or-pinned tensor, flags) for an augmentation parameter set, or (None, 0)."""
+        if aug is None:
+            return None, 0
+        packed = aug if torch.is_tensor(aug) else pack_aug(aug)   # list of ViewAug or sample_packed() output
+        if packed.numel() != 2 * b * 32:
+            raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {packed.numel() // 32}")
+        if packed.is_cuda:
+            return packed, 0
+        # event-guarded ring of pinned buffers that the device reads in place (a staging KERNEL,
+        # not a copy-engine transfer: it cannot queue behind a bulk prefetch of the next batch)
+        slot = self._ring_pos = (self._ring_pos + 1) % len(self._ring_ev)
+        self._ring_ev[slot].synchronize()
+        buf = self._ring[slot][: packed.numel()]
+        buf.copy_(packed)
+        return buf, _lib.PREPROCESS_AUG_HOST
+
+    def _outputs(self, b: int, out: Optional[dict]) -> dict:
+        if out is not None:
+            return out
+        h, w = self.image_size
+        return {
+            "input": torch.empty((b, 6, h, w), device=self.device, dtype=torch.float32),
+            "target": torch.empty((b, 1, h, w), device=self.device, dtype=torch.float32),
+            "valid_mask": torch.empty((b, 1, h, w), device=self.device, dtype=torch.bool),
+        }
+
     def __call__(self, left: torch.Tensor, right: torch.Tensor, disparity: torch.Tensor,
                  aug: Optional[Sequence[ViewAug]] = None, fourterm: bool = False,
                  out: Optional[dict] = None, count_out: Optional[torch.Tensor] = None) -> dict:
@@ -175,31 +202,9 @@ class DevicePreprocessor:
         b, hs, ws, _ = left.shape
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
-        h, w = self.image_size
         left, right, disparity = left.contiguous(), right.contiguous(), disparity.contiguous()
-        if out is None:
-            out = {
-                "input": torch.empty((b, 6, h, w), device=self.device, dtype=torch.float32),
-                "target": torch.empty((b, 1, h, w), device=self.device, dtype=torch.float32),
-                "valid_mask": torch.empty((b, 1, h, w), device=self.device, dtype=torch.bool),
-            }
-        aug_dev = None
-        if aug is not None:
-            packed = aug if torch.is_tensor(aug) else pack_aug(aug)   # list of ViewAug or sample_packed() output
-            if packed.numel() != 2 * b * 32:
-                raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {packed.numel() // 32}")
-            flags_aug = 0
-            if packed.is_cuda:
-                aug_dev = packed
-            else:
-                # event-guarded ring of pinned buffers that the device reads in place (a staging KERNEL,
-                # not a copy-engine transfer: it cannot queue behind a bulk prefetch of the next batch)
-                slot = self._ring_pos = (self._ring_pos + 1) % len(self._ring_ev)
-                self._ring_ev[slot].synchronize()
-                buf = self._ring[slot][: packed.numel()]
-                buf.copy_(packed)
-                aug_dev = buf
-                flags_aug = _lib.PREPROCESS_AUG_HOST
+        out = self._outputs(b, out)
+        aug_dev, flags_aug = self._stage_aug(aug, b)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(
             _lib.load().sdn_preprocess(
@@ -207,7 +212,41 @@ class DevicePreprocessor:
                 aug_dev.data_ptr() if aug_dev is not None else None,
                 out["input"].data_ptr(), out["target"].data_ptr(), out["valid_mask"].data_ptr(),
                 count_out.data_ptr() if count_out is not None else None,
-                (_lib.RESIZE_FOURTERM if fourterm else 0) | (flags_aug if aug_dev is not None else 0), stream,
+                (_lib.RESIZE_FOURTERM if fourterm else 0) | flags_aug, stream,
+            )
+        )
+        if aug_dev is not None and not aug_dev.is_cuda:
+            self._ring_ev[self._ring_pos].record(torch.cuda.current_stream(self.device))
+        return out
+
+    def from_cache(self, left: torch.Tensor, right: torch.Tensor, disparity: torch.Tensor,
+                   aug: Optional[Sequence[ViewAug]] = None, out: Optional[dict] = None,
+                   count_out: Optional[torch.Tensor] = None) -> dict:
+        """The reference's npz read-through cache format (dataset.py:86-128): ``left`` / ``right`` uint8
+        [B,H,W,3] and ``disparity`` float16 [B,H,W], ALREADY at this preprocessor's resolution (the arrays of
+        the ``.npz`` entries, stacked and copied to the GPU).  No resize, no disparity rescale."""
+        h, w = self.image_size
+        for name, t in (("left", left), ("right", right)):
+            if t.dtype != torch.uint8 or not t.is_cuda or t.dim() != 4 or tuple(t.shape[1:]) != (h, w, 3):
+                raise ValueError(f"{name} must be a CUDA uint8 tensor [B,{h},{w},3], got {t.dtype} {tuple(t.shape)}")
+        b = left.shape[0]
+        if disparity.dtype != torch.float16 or not disparity.is_cuda or tuple(disparity.shape) != (b, h, w):
+            raise ValueError(f"disparity must be a CUDA float16 tensor [{b},{h},{w}] (the cache stores float16), "
+                             f"got {disparity.dtype} {tuple(disparity.shape)}")
+        if right.shape != left.shape:
+            raise ValueError("left and right must have the same shape")
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        left, right, disparity = left.contiguous(), right.contiguous(), disparity.contiguous()
+        out = self._outputs(b, out)
+        aug_dev, flags_aug = self._stage_aug(aug, b)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(
+            _lib.load().sdn_preprocess_cached(
+                self.ctx, left.data_ptr(), right.data_ptr(), disparity.data_ptr(), b,
+                aug_dev.data_ptr() if aug_dev is not None else None,
+                out["input"].data_ptr(), out["target"].data_ptr(), out["valid_mask"].data_ptr(),
+                count_out.data_ptr() if count_out is not None else None, flags_aug, stream,
             )
         )
         if aug_dev is not None and not aug_dev.is_cuda:

@@ -12,6 +12,9 @@ What is captured (reference = sdfgeoff/stereo_depth_estimation):
   model.npz      StereoUNet (model.py) seed 42: train- and eval-mode outputs, loss,
                  per-parameter gradient digests, updated BatchNorm buffers
   epoch.npz      run_epoch (train.py:292-418) + AdamW over two synthetic batches
+  live_cached.npz  rows N3 / N4: save_cached_sample -> load_cached_sample -> __getitem__ on a cache hit
+                 (dataset.py:86-128, 272-311), and the live viewer's preprocess_rgb (cv2 fixed-point resize),
+                 disparity_to_depth, confidence_from_logvar (live_camera/depth_live_dl.py:225-229, 371-381)
 """
 from __future__ import annotations
 
@@ -166,13 +169,64 @@ def make_epoch(ref_model, ref_train) -> None:
     )
 
 
+def make_live_cached(ref_dataset) -> None:
+    from live_camera import depth_live_dl as live  # the reference's viewer module (needs cv2)
+
+    rng = np.random.default_rng(21)
+    # N3: a sample written to and read back from the reference's npz cache
+    left, right, disp = synth_triplet(rng, 54, 96)
+    h, w = 32, 48
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        base = tmp / "scene_00" / "dataset" / "data"
+        for sub in ("left/rgb", "right/rgb", "left/disparity"):
+            (base / sub).mkdir(parents=True)
+        Image.fromarray(left, mode="RGB").save(base / "left/rgb/000001.png")
+        Image.fromarray(right, mode="RGB").save(base / "right/rgb/000001.png")
+        Image.fromarray(disp, mode="RGB").save(base / "left/disparity/000001.png")
+        samples = ref_dataset.discover_samples(tmp)
+        cache = tmp / "cache"
+        ds = ref_dataset.FoundationStereoDataset(samples, image_size=(h, w), cache_root=cache)
+        first = ds[0]                                   # miss: computes and writes the cache entry
+        entry = cache / ref_dataset.sample_cache_relpath(samples[0])
+        with np.load(entry) as z:
+            c_left, c_right, c_disp = z["left"], z["right"], z["disparity"]
+        hit = ref_dataset.FoundationStereoDataset(samples, image_size=(h, w), cache_root=cache, require_cache=True)[0]
+    # N4: live pre / post on synthetic camera frames
+    # (small frames keep the fixture small; the arithmetic does not depend on the size: 2.0x down, a ragged
+    # ratio, and an upsample; model size (64, 48) as (width, height))
+    frames = {"f2x": rng.integers(0, 256, (2, 96, 128, 3), dtype=np.uint8),
+              "fragged": rng.integers(0, 256, (2, 61, 77, 3), dtype=np.uint8),
+              "fup": rng.integers(0, 256, (2, 24, 32, 3), dtype=np.uint8)}
+    pre = {k: np.stack([live.preprocess_rgb(v[0], (64, 48)).numpy(), live.preprocess_rgb(v[1], (64, 48)).numpy()])
+           for k, v in frames.items()}
+    d = (rng.random((48, 64)).astype(np.float32) * 40.0)
+    d[:5] = 0.0
+    d[30, 7] = np.nan
+    d[31, 7] = 5e-7
+    lv = rng.random((48, 64)).astype(np.float32) * 9.0 - 6.0
+    np.savez_compressed(
+        OUT / "live_cached.npz",
+        cache_left=c_left, cache_right=c_right, cache_disp=c_disp, cache_hw=np.array([h, w]),
+        miss_input=first["input"].numpy(), hit_input=hit["input"].numpy(), hit_target=hit["target"].numpy(),
+        hit_mask=hit["valid_mask"].numpy(),
+        **{"frames_" + k: v for k, v in frames.items()}, **{"pre_" + k: v for k, v in pre.items()},
+        disparity=d, logvar=lv, focal=np.float64(244.435), baseline=np.float64(0.0715),
+        depth=live.disparity_to_depth(d, 244.435, 0.0715), confidence=live.confidence_from_logvar(lv),
+    )
+
+
 def main() -> None:
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     ref_dataset, ref_model, ref_train = import_reference()
+    if "--only-live-cached" in sys.argv:
+        make_live_cached(ref_dataset)
+        return
     make_samples(ref_dataset)
     make_augment(ref_dataset)
     make_model(ref_model)
     make_epoch(ref_model, ref_train)
+    make_live_cached(ref_dataset)
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -613,3 +613,103 @@ def test_source_prefetcher_delivers_batches_in_order(dev):
         done()
         seen += 1
     assert seen == 5
+
+
+# ------------------------------------------------------------ rows N3 / N4
+def test_cached_sample_path_bit_exact(dev):
+    """Row N3: the npz-cache sample format (uint8 HWC views + float16 disparity at model resolution,
+    dataset.py:86-128) through sdn_preprocess_cached: fixture written by the real reference, then a batch."""
+    from stereo_depth_estimation_b200.preprocess import DevicePreprocessor, ViewAug
+
+    f = np.load(os.path.join(GOLDEN, "live_cached.npz"))
+    h, w = (int(v) for v in f["cache_hw"])
+    pre = DevicePreprocessor(dev, 4, (h, w))
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    args = [torch.from_numpy(f[k][None]).to(dev) for k in ("cache_left", "cache_right", "cache_disp")]
+    out = pre.from_cache(*args, count_out=cnt)
+    assert np.array_equal(out["input"][0].cpu().numpy(), f["hit_input"])
+    assert np.array_equal(out["target"][0].cpu().numpy(), f["hit_target"])
+    assert np.array_equal(out["valid_mask"][0].cpu().numpy(), f["hit_mask"])
+    assert int(cnt.item()) == int(f["hit_mask"].sum())
+    # a ragged batch with augmentation, an all-invalid sample and non-finite cache values
+    rng = np.random.default_rng(4)
+    b = 3
+    L = rng.integers(0, 256, (b, h, w, 3), dtype=np.uint8)
+    R = rng.integers(0, 256, (b, h, w, 3), dtype=np.uint8)
+    D = (rng.random((b, h, w)) * 70000.0 - 100.0).astype(np.float16)     # negatives, > 65504 -> +inf
+    D[1] = 0
+    views = [ViewAug(1.1, 0.85, 1.2, 0.05, 0.9), ViewAug(0.8, 1.2, 0.8, -0.09, 1.2, blur_sigma=0.7), ViewAug(), ViewAug(),
+             ViewAug(0.9, 1.1, 0.0, -0.5, 1.0), ViewAug(1.0, 1.0, 1.0, 0.0, 1.0, blur_sigma=0.4)]
+    dev_args = [torch.from_numpy(a).to(dev) for a in (L, R, D)]
+    plain = pre.from_cache(*dev_args, count_out=cnt)
+    total = 0
+    for i in range(b):
+        ref = so.cached_sample(L[i], R[i], D[i])
+        assert np.array_equal(plain["input"][i].cpu().numpy(), ref["input"])
+        assert np.array_equal(plain["target"][i].cpu().numpy(), ref["target"])
+        assert np.array_equal(plain["valid_mask"][i].cpu().numpy(), ref["valid_mask"])
+        total += int((ref["valid_mask"] & np.isfinite(ref["target"])).sum())
+    assert int(cnt.item()) == total and np.isinf(plain["target"].cpu().numpy()).any()
+    aug_out = pre.from_cache(*dev_args, aug=views)
+    for i in range(b):
+        aug = [dict(brightness=v.brightness, contrast=v.contrast, saturation=v.saturation, hue=v.hue, gamma=v.gamma,
+                    blur_sigma=v.blur_sigma) for v in views[2 * i: 2 * i + 2]]
+        ref = so.cached_sample(L[i], R[i], D[i], aug=aug)
+        np.testing.assert_allclose(aug_out["input"][i].cpu().numpy(), ref["input"], atol=1e-5, rtol=0)
+    with pytest.raises(ValueError):
+        pre.from_cache(dev_args[0], dev_args[1], dev_args[2].float())
+
+
+@pytest.mark.parametrize("hs,ws", [(480, 640), (720, 1280), (123, 457), (120, 160)])
+def test_live_preprocess_bit_exact(dev, hs, ws):
+    """Row N4: preprocess_rgb x 2 + cat (depth_live_dl.py:225-229, 516-520) on the device; OpenCV's uint8
+    INTER_LINEAR fixed-point arithmetic must be reproduced bit for bit (oracle, and cv2 itself when present)."""
+    from stereo_depth_estimation_b200 import LivePipeline, StereoUNet
+
+    model = StereoUNet().to(dev)
+    live = LivePipeline(model, model_size=(320, 240))
+    rng = np.random.default_rng(hs)
+    view_l = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+    view_r = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+    x = live.preprocess(view_l, view_r).cpu().numpy()
+    assert np.array_equal(x, so.live_model_input(view_l, view_r, (320, 240)))
+    try:
+        import cv2
+    except ImportError:
+        return
+    for v, view in enumerate((view_l, view_r)):
+        want = cv2.resize(cv2.cvtColor(view, cv2.COLOR_BGR2RGB), (320, 240), interpolation=cv2.INTER_LINEAR)
+        want = (torch.from_numpy(want).float().permute(2, 0, 1) / 255.0).numpy()        # depth_live_dl.py:228
+        assert np.array_equal(x[0, 3 * v: 3 * v + 3], want)
+
+
+def test_live_fixture_and_postprocess(dev):
+    """Fixture produced by the real reference (cv2 resize at three scale ratios; disparity_to_depth,
+    confidence_from_logvar, depth_live_dl.py:371-381) and the EMA recurrence (:531-538) over three frames."""
+    from stereo_depth_estimation_b200 import LivePipeline, StereoUNet
+
+    f = np.load(os.path.join(GOLDEN, "live_cached.npz"))
+    model = StereoUNet().to(dev)
+    live = LivePipeline(model, model_size=(64, 48), ema_alpha=0.25, focal_length_px=float(f["focal"]),
+                        baseline_m=float(f["baseline"]))
+    for key in ("f2x", "fragged", "fup"):
+        frames = f["frames_" + key]
+        x = live.preprocess(frames[0], frames[1]).cpu().numpy()
+        assert np.array_equal(x[0, :3], f["pre_" + key][0]) and np.array_equal(x[0, 3:], f["pre_" + key][1]), key
+    d0 = f["disparity"]
+    lv = torch.from_numpy(f["logvar"]).to(dev)
+    smoothed = None
+    for frame in range(3):
+        d = d0 * np.float32(1.0 + 0.1 * frame)
+        maps = live.postprocess(torch.from_numpy(d).to(dev), lv).cpu().numpy()
+        smoothed = so.ema_update(smoothed, d, 0.25)
+        assert np.array_equal(maps[0], smoothed, equal_nan=True), frame                       # EMA: bit-exact
+        assert np.array_equal(maps[1], so.disparity_to_depth(smoothed, float(f["focal"]), float(f["baseline"])),
+                              equal_nan=True), frame                                            # one fp32 divide: bit-exact
+        np.testing.assert_allclose(maps[2], f["confidence"], rtol=2e-6)                        # expf: ulps
+    plain = LivePipeline(model, model_size=(64, 48))            # no EMA, no calibration
+    maps = plain.postprocess(torch.from_numpy(d0).to(dev), lv).cpu().numpy()
+    assert np.array_equal(maps[0], d0, equal_nan=True) and np.isnan(maps[1]).all()
+    live.reset()
+    maps = live.postprocess(torch.from_numpy(d0).to(dev), lv).cpu().numpy()
+    assert np.array_equal(maps[1], f["depth"], equal_nan=True)

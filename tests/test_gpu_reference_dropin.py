@@ -264,6 +264,48 @@ def test_reference_live_call_sequence_verbatim(dev, ref):
         assert np.isfinite(depth[p_o > 1e-6]).all() and (conf > 0).all()
 
 
+def test_live_pipeline_matches_reference_loop(dev, ref):
+    """Row N4 end to end: LivePipeline (device pre -> graph-replayed model -> device post, one D2H) against the
+    reference's per-frame host code (depth_live_dl.py:516-538, 371-381) driving the REFERENCE model."""
+    _, model_mod, _ = ref
+    live_mod = refenv.load_live()
+    from stereo_depth_estimation_b200 import LivePipeline
+
+    ref_model, ours = pair_of_models(model_mod, dev)
+    ref_model.train()
+    with torch.no_grad():
+        for b in cpu_batches(3, 2, 240, 320, seed=5):
+            ref_model(b["input"].to(dev))
+    ours.load_state_dict(ref_model.state_dict())
+    ref_model.eval()
+    focal, baseline, alpha = 488.87 * 320 / 640, 0.0715, 0.4        # calibration/stereo_calib.npz, rescaled
+    pipe = LivePipeline(ours, model_size=(320, 240), ema_alpha=alpha, focal_length_px=focal, baseline_m=baseline)
+    rng = np.random.default_rng(12)
+    smoothed = None
+    for frame in range(3):
+        view_l = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+        view_r = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+        got = pipe(view_l, view_r)
+        # ---- the reference's host code on the reference model ----
+        left_tensor = live_mod.preprocess_rgb(view_l, (320, 240))
+        right_tensor = live_mod.preprocess_rgb(view_r, (320, 240))
+        model_input = torch.cat([left_tensor, right_tensor], dim=0).unsqueeze(0).to(dev)
+        with torch.inference_mode():
+            disparity_tensor, logvar_tensor = ref_model(model_input, return_uncertainty=True)
+            prediction = disparity_tensor[0, 0].detach().cpu().numpy().astype(np.float32)
+            logvar = logvar_tensor[0, 0].detach().cpu().numpy().astype(np.float32)
+        smoothed = prediction if smoothed is None else (alpha * prediction + (1.0 - alpha) * smoothed)
+        depth_m = live_mod.disparity_to_depth(smoothed, float(focal), float(baseline))
+        confidence = live_mod.confidence_from_logvar(logvar)
+        # ----
+        assert np.array_equal(pipe._input.cpu().numpy(), model_input.cpu().numpy())        # device pre: bit-exact
+        for name, a, r in (("disparity", got["disparity"], smoothed), ("logvar", got["logvar"], logvar),
+                           ("depth", got["depth"], depth_m), ("confidence", got["confidence"], confidence)):
+            e = float(np.nanmax(np.abs(a - r)) / np.nanmax(np.abs(r)))
+            assert a.shape == (240, 320) and e <= 1e-2, (frame, name, e)
+            assert np.array_equal(np.isnan(a), np.isnan(r)), (frame, name)
+
+
 def test_reference_previews_on_dropin(dev, ref, tmp_path):
     train, model_mod, _ = ref
     _, ours = pair_of_models(model_mod, dev)

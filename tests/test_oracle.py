@@ -163,3 +163,52 @@ def test_run_epoch_matches_reference():
     for key, want in zip(so.param_keys(sd), f["param_digests"]):
         p = sd[key].double().flatten()
         assert p.norm().item() == pytest.approx(want[0], rel=1e-3), key
+
+
+# ------------------------------------------------------------------ rows N3 / N4
+def test_cached_sample_matches_reference_cache_hit():
+    """dataset.py:86-128, 272-311: the fixture holds the arrays the REAL reference wrote into its npz cache and
+    the sample it returned on the cache hit."""
+    f = g("live_cached.npz")
+    got = so.cached_sample(f["cache_left"], f["cache_right"], f["cache_disp"])
+    assert f["cache_disp"].dtype == np.float16 and f["cache_left"].dtype == np.uint8
+    assert np.array_equal(got["input"], f["hit_input"])
+    assert np.array_equal(got["target"], f["hit_target"])
+    assert np.array_equal(got["valid_mask"], f["hit_mask"])
+    # and the writer side: what save_cached_sample stores for the freshly computed sample
+    l8, r8, d16 = so.to_cache_format(f["miss_input"][:3], f["miss_input"][3:], f["hit_target"])
+    assert np.array_equal(l8, f["cache_left"]) and np.array_equal(r8, f["cache_right"])
+    assert np.array_equal(d16, f["cache_disp"])
+
+
+def test_live_pre_post_match_reference_fixture():
+    """live_camera/depth_live_dl.py:225-229, 371-381 through the fixture produced by the real reference (cv2)."""
+    f = g("live_cached.npz")
+    for key in ("f2x", "fragged", "fup"):
+        frames = f["frames_" + key]
+        for v in range(2):
+            assert np.array_equal(so.live_preprocess_rgb(frames[v], (64, 48)), f["pre_" + key][v]), (key, v)
+        x = so.live_model_input(frames[0], frames[1], (64, 48))
+        assert x.shape == (1, 6, 48, 64) and x.dtype == np.float32
+    depth = so.disparity_to_depth(f["disparity"], float(f["focal"]), float(f["baseline"]))
+    assert np.array_equal(depth, f["depth"], equal_nan=True)
+    assert np.isnan(depth[:5]).all() and np.isnan(depth[30, 7]) and np.isnan(depth[31, 7])
+    np.testing.assert_allclose(so.confidence_from_logvar(f["logvar"]), f["confidence"], rtol=1e-6)
+    p = f["disparity"]
+    assert so.ema_update(None, p, 0.4) is p and so.ema_update(p, p, 0.0) is p
+    np.testing.assert_array_equal(so.ema_update(p * 2, p, 0.25), (0.25 * p + 0.75 * (p * 2)).astype(np.float32))
+
+
+def test_cv_resize_restatement_is_bit_exact_against_cv2():
+    """The third-party algorithm itself: cv2.resize(INTER_LINEAR) on uint8 (opencv-python 4.13), many shapes."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    shapes = [((480, 640), (320, 240)), ((720, 1280), (320, 240)), ((240, 320), (640, 480)), ((123, 457), (320, 240)),
+              ((481, 641), (320, 240)), ((100, 100), (333, 77)), ((7, 9), (64, 48)), ((33, 47), (31, 29))]
+    for _ in range(8):
+        shapes.append(((int(rng.integers(5, 200)), int(rng.integers(5, 200))),
+                       (int(rng.integers(4, 160)), int(rng.integers(4, 160)))))
+    for (h, w), (dw, dh) in shapes:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(so.cv_resize_linear_u8(src, (dw, dh)), want), ((h, w), (dw, dh))
