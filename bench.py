@@ -401,6 +401,9 @@ def run_b200(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from stereo_depth_estimation_b200.pipeline import bind_host_to_gpu
+
+    numa_cpus = bind_host_to_gpu(dev) if world > 1 else None     # before any pinned allocation (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -653,7 +656,8 @@ def run_b200(args):
                                    "540x960 sources -> preprocess -> fwd -> loss -> bwd -> allreduce -> AdamW"
                                    % (args.global_batch, b_local),
                        "global_batch": args.global_batch, "parallelism": f"dp{world}",
-                       "l2": "inputs larger than L2 (%.2f GB of uint8 sources per rank per step)" % (h2d_bytes / 1e9)},
+                       "l2": "inputs larger than L2 (%.2f GB of uint8 sources per rank per step)" % (h2d_bytes / 1e9),
+                       "host_affinity": ("rank 0 bound to %d GPU-local cores" % len(numa_cpus)) if numa_cpus else "unbound"},
             "model_tflops": value * TRAIN_FLOPS_PER_PAIR / 1e12,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_copy_ms_alone": h2d_copy_ms, "h2d_bytes_per_step": h2d_bytes * world,

@@ -30,7 +30,7 @@ typedef struct sdn_ctx sdn_ctx;
 
 #define SDN_NUM_PARAMS 66 /* len(list(StereoUNet().parameters())), model.py:59-77 */
 #define SDN_NUM_BN 18     /* BatchNorm2d layers, model.py:37,40 (x9 blocks) */
-#define SDN_NUM_STAGES 4  /* backward stages == gradient all-reduce buckets */
+#define SDN_NUM_STAGES 5  /* backward stages == gradient all-reduce buckets */
 
 /* Per-view photometric augmentation parameters, the explicit form of the
  * reference samplers dataset.py:214-246 consumed by dataset.py:248-270. */
@@ -103,7 +103,7 @@ int sdn_count_valid(sdn_ctx* ctx, const float* target, const uint8_t* valid_mask
  * optimizer.step(), which is sdn_adamw_step): train-mode forward -> n = sum(valid_mask & isfinite(target))
  * (skipped with SDN_STEP_HAVE_COUNT: *n_norm already holds this rank's count, e.g. from sdn_preprocess) ->
  * [all-reduce of n: the loss normaliser is the GLOBAL valid count] -> fused loss, metric sums and head
- * backward (sdn_loss_begin semantics: sums4 / count accumulate) -> the four backward stages; with a
+ * backward (sdn_loss_begin semantics: sums4 / count accumulate) -> the SDN_NUM_STAGES backward stages; with a
  * communicator (sdn_comm_init) each stage's gradient bucket is all-reduced (sum) on the context's
  * communicator stream while the next stage runs, and `stream` waits for the last bucket before the call's
  * work ends.  Gradients go to the destinations given to sdn_set_params; for data parallelism the

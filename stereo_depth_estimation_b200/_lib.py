@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 NUM_PARAMS = 66
 NUM_BN = 18
-NUM_STAGES = 4
+NUM_STAGES = 5
 RESIZE_FOURTERM = 1
 PREPROCESS_AUG_HOST = 4
 CTX_PREPROCESS_ONLY = 1

@@ -1653,8 +1653,10 @@ int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* 
 }
 
 int sdn_stage_param_range(int stage, int* first, int* num) {
-    static const int f[SDN_NUM_STAGES] = {38, 30, 24, 0};
-    static const int n[SDN_NUM_STAGES] = {28, 8, 6, 24};
+    // heads + dec1..dec3 + up1..up3 | dec4 + up4 | bottleneck | enc4 + enc3 | enc2 + enc1.  The last bucket is the
+    // only one whose all-reduce cannot hide behind later backward work, so it is the smallest (0.26 MB).
+    static const int f[SDN_NUM_STAGES] = {38, 30, 24, 12, 0};
+    static const int n[SDN_NUM_STAGES] = {28, 8, 6, 12, 12};
     if (stage < 0 || stage >= SDN_NUM_STAGES || first == nullptr || num == nullptr)
         return fail("sdn_stage_param_range: bad stage %d", stage);
     *first = f[stage];
@@ -1680,8 +1682,11 @@ int sdn_backward_stage(sdn_ctx* c, int stage, void* stream) {
         case 2:  // bottleneck
             SDN_OK(conv_backward(c, 9, B, st)); SDN_OK(conv_backward(c, 8, B, st));
             break;
-        case 3:  // enc4 .. enc1
-            for (int i = 7; i >= 0; --i) SDN_OK(conv_backward(c, i, B, st));
+        case 3:  // enc4, enc3
+            for (int i = 7; i >= 4; --i) SDN_OK(conv_backward(c, i, B, st));
+            break;
+        case 4:  // enc2, enc1
+            for (int i = 3; i >= 0; --i) SDN_OK(conv_backward(c, i, B, st));
             break;
         default:
             return fail("sdn_backward_stage: bad stage %d", stage);
@@ -1767,14 +1772,26 @@ int sdn_train_step(sdn_ctx* c, const float* x, const float* target, const uint8_
     long long bucket_n[SDN_NUM_STAGES] = {};
     if (dp)
         for (int s = 0; s < SDN_NUM_STAGES; ++s) SDN_OK(stage_bucket(c, s, &bucket[s], &bucket_n[s]));
+    const bool overlap = dp && !(flags & SDN_STEP_NO_OVERLAP) && !c->prof;
+    // The loss normaliser is the GLOBAL valid count.  It depends only on the batch, so its all-reduce (8 bytes, but a
+    // rendezvous of all ranks) runs on the communicator stream UNDER the forward; the main stream picks it up right
+    // before the loss kernel.  On the main stream it would make every rank wait for the slowest one after each forward.
+    const bool count_early = overlap && (flags & SDN_STEP_HAVE_COUNT);
+    if (count_early) {
+        CUDA_OK(cudaEventRecord(c->ev_bucket, st));
+        CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_bucket, 0));
+        NCCL_OK(g_nccl.AllReduce(n_norm, n_norm, 1, ncclUint64, ncclSum, c->comm, c->comm_stream));
+        CUDA_OK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    }
     SDN_OK(forward_impl(c, x, nullptr, nullptr, B, 1, params_dirty, st));
     if (!(flags & SDN_STEP_HAVE_COUNT)) SDN_OK(sdn_count_valid(c, target, mask, B, n_norm, stream));
-    if (dp) {
+    if (count_early) {
+        CUDA_OK(cudaStreamWaitEvent(st, c->ev_comm, 0));
+    } else if (dp) {
         ProfScope ps(c, st, "allreduce_count", 0, 0.0, 8.0);
         NCCL_OK(g_nccl.AllReduce(n_norm, n_norm, 1, ncclUint64, ncclSum, c->comm, st));
     }
     SDN_OK(sdn_loss_begin(c, target, mask, nullptr, nullptr, sums4, count, n_norm, 1, 0, stream));
-    const bool overlap = dp && !(flags & SDN_STEP_NO_OVERLAP) && !c->prof;
     for (int s = 0; s < SDN_NUM_STAGES; ++s) {
         SDN_OK(sdn_backward_stage(c, s, stream));
         if (!dp) continue;

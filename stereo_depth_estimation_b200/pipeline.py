@@ -15,9 +15,36 @@ transfer and hides completely behind a step that is longer than it::
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, Iterator, Sequence, Tuple
+import os
+from typing import Callable, Iterable, Iterator, Optional, Sequence, Tuple
 
 import torch
+
+
+def bind_host_to_gpu(device: torch.device) -> Optional[list]:
+    """Pin this process (and therefore the pages it first-touches, pinned staging buffers included) to the CPU
+    cores NVML reports as local to ``device``.  One process per GPU under ``torchrun`` otherwise floats over both
+    sockets, and at 8 ranks x 149 MB of uint8 sources per step the host -> device copies cross the inter-socket
+    link and stop hiding behind the step (measured: end-to-end 8-GPU efficiency 0.70).  Call it BEFORE allocating
+    the host buffers.  Returns the CPU list, or None when NVML / the affinity call is unavailable (no-op)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        dev = torch.device(device)
+        props = torch.cuda.get_device_properties(dev)
+        bus_id = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1 and 64 * w + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 class SourcePrefetcher:

@@ -16,7 +16,7 @@ module is the second entry point (level B2):
 Data parallelism (one process per GPU, ``torch.distributed``): the batch is
 sharded by the caller; the loss normaliser is the GLOBAL valid count (all-reduced
 while the forward runs) so the sum of per-rank gradients equals the
-single-process gradient exactly; the 4 backward stages are the all-reduce
+single-process gradient exactly; the backward stages (5) are the all-reduce
 buckets, issued on a side stream as soon as each stage's kernels are enqueued so
 NCCL overlaps the rest of the backward.  BatchNorm statistics stay per rank
 (standard DDP semantics).

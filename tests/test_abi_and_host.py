@@ -113,7 +113,8 @@ def test_stage_slices_cover_flat_gradient_buffer():
     assert sorted(sl)[0][0] == 0 and sorted(sl)[-1][1] == total
     assert sum(hi - lo for lo, hi in sl) == total
     # backward order: decoder tail first, encoder last; bottleneck is the 14 MB bucket
-    assert sl[3][0] == 0 and (sl[2][1] - sl[2][0]) == 256 * 512 * 9 + 512 * 512 * 9 + 4 * 512
+    assert sl[4][0] == 0 and (sl[2][1] - sl[2][0]) == 256 * 512 * 9 + 512 * 512 * 9 + 4 * 512
+    assert sl[4][1] == sl[3][0] and (sl[4][1] - sl[4][0]) * 4 < 300_000     # the exposed last bucket is the smallest
 
 
 def _dp_worker(rank, world, port, out):
