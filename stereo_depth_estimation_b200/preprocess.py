@@ -172,6 +172,9 @@ class DevicePreprocessor:
             raise ValueError(f"need 2*B = {2 * b} view parameter sets, got {packed.numel() // 32}")
         if packed.is_cuda:
             return packed, 0
+        if packed.is_pinned():
+            # the caller owns a pinned buffer and its lifetime (GraphedTrainStep: one per captured graph)
+            return packed, _lib.PREPROCESS_AUG_HOST
         # event-guarded ring of pinned buffers that the device reads in place (a staging KERNEL,
         # not a copy-engine transfer: it cannot queue behind a bulk prefetch of the next batch)
         slot = self._ring_pos = (self._ring_pos + 1) % len(self._ring_ev)
@@ -215,7 +218,7 @@ class DevicePreprocessor:
                 (_lib.RESIZE_FOURTERM if fourterm else 0) | flags_aug, stream,
             )
         )
-        if aug_dev is not None and not aug_dev.is_cuda:
+        if aug_dev is not None and not aug_dev.is_cuda and not (torch.is_tensor(aug) and aug.is_pinned()):
             self._ring_ev[self._ring_pos].record(torch.cuda.current_stream(self.device))
         return out
 

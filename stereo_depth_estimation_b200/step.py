@@ -197,6 +197,75 @@ class FusedStep:
         return (disp, logvar) if want_outputs else None
 
 
+class GraphedTrainStep:
+    """The whole train step - device input pipeline, ``sdn_train_step`` (forward, fused loss, backward, bucketed
+    all-reduce on the library's communicator) and ``FusedAdamW`` - captured ONCE per source-buffer set as a CUDA
+    graph and replayed: ~210 kernel launches become one ``cudaGraphLaunch`` per step.  It pays where the per-GPU
+    batch is small (32 pairs per GPU in the 8-GPU run: the step is 6 ms and the gaps between its kernels show).
+
+    A graph bakes device addresses in, so one graph is kept per (left, right, disparity) buffer triple - the two
+    slots of ``SourcePrefetcher`` give two graphs - together with its own pinned augmentation-parameter buffer, which
+    the staging kernel inside the graph reads in place.  The first call for a triple runs eagerly (it also warms the
+    library up), the second captures, later ones replay.  Needs ``FusedAdamW`` (the skip-empty-batch rule is on the
+    device; a host-side ``optimizer.step()`` cannot be captured)."""
+
+    def __init__(self, step: "FusedStep", pre, out: Optional[dict] = None) -> None:
+        if not isinstance(step.optimizer, FusedAdamW):
+            raise ValueError("GraphedTrainStep needs FusedAdamW (the optimizer step is part of the graph)")
+        self.step, self.pre = step, pre
+        self.out = out
+        self.count = None
+        self.entries = {}      # (ptrs, parity) -> dict(graph, aug, event, calls)
+        self.turns = {}
+
+    def __call__(self, left: torch.Tensor, right: torch.Tensor, disparity: torch.Tensor, aug: torch.Tensor) -> None:
+        """``aug``: host uint8 tensor from ``AugmentSampler.sample_packed`` (2*B parameter sets)."""
+        dev = left.device
+        if self.count is None:
+            self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        base = (left.data_ptr(), right.data_ptr(), disparity.data_ptr(), tuple(left.shape))
+        # two graphs (two pinned parameter buffers) per buffer triple, used alternately: the host may prepare step
+        # k+1 while step k still runs, it only waits for the replay of two steps ago to have read its parameters
+        turn = self.turns.get(base, 0)
+        self.turns[base] = turn + 1
+        key = base + (turn & 1,)
+        ent = self.entries.get(key)
+        if ent is None:
+            ent = {"graph": None, "aug": torch.empty(aug.numel(), dtype=torch.uint8).pin_memory(),
+                   "event": torch.cuda.Event(), "calls": 0}
+            self.entries[key] = ent
+        ent["event"].synchronize()           # the previous replay of THIS graph has read its parameter buffer
+        ent["aug"].copy_(aug)
+        stream = torch.cuda.current_stream(dev)
+
+        def body():
+            self.out = self.pre(left, right, disparity, aug=ent["aug"], out=self.out, count_out=self.count)
+            self.step.train_step(self.out, valid_count=self.count)
+
+        if ent["graph"] is None and ent["calls"] >= 1:
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            ent["graph"] = graph
+        if ent["graph"] is not None:
+            ent["graph"].replay()
+            # the graph updated the parameters behind Python's back: the packed operand cache is stale for
+            # whoever calls the module next (the captured step re-packs on every replay by construction)
+            eng = self.step.model._engine
+            eng.packed_versions = None
+            eng.generation += 1
+        else:
+            body()
+        ent["calls"] += 1
+        ent["event"].record(stream)
+
+    @property
+    def warmup_calls(self) -> int:
+        """Calls per buffer triple before every step is a replay (2 eager + 2 capturing)."""
+        return 4
+
+
 def _metrics(tot: Dict[str, float]) -> Dict[str, float]:
     n = tot["count"]
     return {

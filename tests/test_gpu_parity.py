@@ -713,3 +713,52 @@ def test_live_fixture_and_postprocess(dev):
     live.reset()
     maps = live.postprocess(torch.from_numpy(d0).to(dev), lv).cpu().numpy()
     assert np.array_equal(maps[1], f["depth"], equal_nan=True)
+
+
+def test_graphed_train_step_matches_eager(dev):
+    """GraphedTrainStep (whole step replayed as a CUDA graph) against the same steps launched eagerly: same
+    sources, same augmentation parameters, same seed; only the order of the fp32 wgrad atomics differs."""
+    from stereo_depth_estimation_b200.optim import FusedAdamW
+    from stereo_depth_estimation_b200.preprocess import AugmentSampler, DevicePreprocessor
+    from stereo_depth_estimation_b200.step import FusedStep, GraphedTrainStep
+
+    rng = np.random.default_rng(8)
+    b, h, w = 2, 64, 96
+    srcs = [torch.from_numpy(a).to(dev) for a in synth_sources(rng, b, 108, 192)]
+    augs = [AugmentSampler(seed=3).sample_packed(b) for _ in range(7)]
+    results = []
+    for graphed in (False, True):
+        model, sd = fresh_model(dev)
+        step = FusedStep(model, FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4))
+        pre = DevicePreprocessor(dev, b, (h, w))
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        g = GraphedTrainStep(step, pre) if graphed else None
+        out = None
+        for aug in augs:
+            if g is not None:
+                g(srcs[0], srcs[1], srcs[2], aug)
+            else:
+                out = pre(srcs[0], srcs[1], srcs[2], aug=aug, out=out, count_out=count)
+                step.train_step(out, valid_count=count)
+        torch.cuda.synchronize()
+        if g is not None:
+            assert sum(e["graph"] is not None for e in g.entries.values()) == 2      # both parities captured
+        results.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, step.read_metrics(), sd))
+        # the module still works after replays (operand cache refreshed): eval forward vs the oracle at these weights
+        model.eval()
+        x = make_batch(dev, 1, h, w, seed=9)["input"]
+        with torch.inference_mode():
+            d = model(x)
+        rd, _ = so.model_forward(results[-1][0], x, False, True)
+        assert (d - rd).abs().max().item() / rd.abs().max().item() <= 1e-2
+    (pa, ma, sd), (pb, mb, _) = results
+    assert ma["count"] == mb["count"] > 0
+    for k in ("nll", "abs", "sq", "sigma"):
+        assert mb[k] == pytest.approx(ma[k], rel=1e-4), k
+    for k in pa:
+        if so.is_param_key(k) and pa[k].numel() > 1:
+            ua, ub = (pa[k] - sd[k]).flatten().double(), (pb[k] - sd[k]).flatten().double()
+            cos = float(torch.dot(ua, ub) / (ua.norm() * ub.norm()).clamp(min=1e-30))
+            assert cos > 0.999, (k, cos)
+        elif "num_batches" in k:
+            assert int(pa[k]) == int(pb[k]) == 7
