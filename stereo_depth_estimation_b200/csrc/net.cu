@@ -1401,16 +1401,17 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
     // shared-memory staged kernel when the source rows are 16-byte aligned and the footprint fits
     const int max_rows = (int)std::ceil((double)PRE_ROWS * Hs / H) + 3;
     const int row_bytes = (((int)std::ceil(128.0 * Ws / W) + 3) * 3 + 47) & ~15;
-    const size_t pre_smem = (size_t)3 * max_rows * row_bytes;
+    const size_t pre_smem = (size_t)3 * max_rows * row_bytes;      // one tile buffer: one tile per CTA (see the kernel)
     const bool aligned = ((Ws * 3) % 16 == 0) && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)disparity) % 16 == 0);
     const bool staged = aligned && pre_smem <= 200 * 1024 && !(flags & SDN_PREPROCESS_DIRECT);
     if (staged) {
+        const int grid = parts * B;
         if (flags & SDN_RESIZE_FOURTERM)
-            launch_k(decode_resize_smem_kernel<true>, dim3(parts, B), 256, pre_smem, st, 
+            launch_k(decode_resize_smem_kernel<true>, grid, PRE_THREADS, pre_smem, st,
                 left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
                 aug ? gray_part : nullptr, parts, max_rows, row_bytes);
         else
-            launch_k(decode_resize_smem_kernel<false>, dim3(parts, B), 256, pre_smem, st, 
+            launch_k(decode_resize_smem_kernel<false>, grid, PRE_THREADS, pre_smem, st,
                 left, right, disparity, B, Hs, Ws, H, W, input, target, mask, valid_count, aug,
                 aug ? gray_part : nullptr, parts, max_rows, row_bytes);
     } else if (flags & SDN_RESIZE_FOURTERM)

@@ -62,8 +62,9 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float e, floa
         const float w00 = __fmul_rn(h0, w0), w01 = __fmul_rn(h0, w1), w10 = __fmul_rn(h1, w0), w11 = __fmul_rn(h1, w1);
         return __fmaf_rn(w11, e, __fmaf_rn(w10, c, __fmaf_rn(w00, a, __fmul_rn(w01, b))));
     }
-    const float top = __fmaf_rn(w0, a, __fmul_rn(w1, b));
-    const float bot = __fmaf_rn(w0, c, __fmul_rn(w1, e));
+    // w1 == 0 implies w0 == 1 (bilinear_src): fma(1, a, 0 * b) == a bit for bit for finite non-negative inputs
+    const float top = w1 == 0.f ? a : __fmaf_rn(w0, a, __fmul_rn(w1, b));
+    const float bot = w1 == 0.f ? c : __fmaf_rn(w0, c, __fmul_rn(w1, e));
     return __fmaf_rn(h0, top, __fmul_rn(h1, bot));
 }
 
@@ -188,150 +189,218 @@ __global__ void __launch_bounds__(128) decode_resize_kernel(
 // to the direct kernel otherwise.  256 threads: 128 output columns x PRE_ROWS rows.
 // u8 / 255 correctly rounded (== the reference's float32 division, dataset.py:185) without a divide or a
 // table: one Newton step on q = b * fl(1/255) is exact for all 256 inputs (checked exhaustively).
+// byte -> float on the FMA pipe: 0x4B000000 | b is the float 8388608 + b exactly (the integer -> float conversion
+// instruction runs on the quarter-rate conversion pipe, and this kernel is instruction-bound)
+__device__ __forceinline__ float byte_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 __device__ __forceinline__ float u8_over_255(uint8_t v) {
-    const float b = (float)v;
+    const float b = byte_to_float(v);
     const float r = 0.003921568859368563f;   // fl(1/255)
     const float q = __fmul_rn(b, r);
     const float rem = __fmaf_rn(-q, 255.f, b);
     return __fmaf_rn(rem, r, q);
 }
 
+// Three consecutive bytes (one HWC pixel) at an arbitrary shared-memory byte address as the low 24 bits of a word:
+// two aligned 32-bit loads and a funnel shift instead of three byte loads (the pixel pitch of 9 bytes between
+// neighbouring threads already costs ~3 wavefronts per load instruction).
+__device__ __forceinline__ uint32_t load_rgb24(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = uint32_t(a & 3) * 8;
+    return __funnelshift_r(w[0], w[1], sh) & 0x00FFFFFFu;
+}
+// depth_uint8_decoding (dataset.py:23-30) of one pixel held as R | G << 8 | B << 16: exact in fp32 (max
+// 16,646,655 < 2^24), then one correctly rounded divide.
+// The quotient s / 1000 without a divide: q = s * fl(1/1000), one Newton correction - bit-identical to the IEEE
+// division for EVERY integer s in [0, 16,646,655] (checked exhaustively on the device, tests/div_probe.cu).
+__device__ __forceinline__ float decode_rgb24(uint32_t px) {
+    const float r = byte_to_float(px & 0xFFu), g = byte_to_float((px >> 8) & 0xFFu), b = byte_to_float(px >> 16);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(r, 255.f), 255.f), __fmul_rn(g, 255.f)), b);
+    const float rcp = 1.0f / 1000.0f;
+    const float q = __fmul_rn(s, rcp);
+    return __fmaf_rn(__fmaf_rn(-q, 1000.f, s), rcp, q);
+}
+
+constexpr int PRE_THREADS = 256;   // 128 output columns x 2 row phases
 template <bool FOURTERM>
-__global__ void __launch_bounds__(256) decode_resize_smem_kernel(
+__global__ void __launch_bounds__(PRE_THREADS) decode_resize_smem_kernel(
     const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, const uint8_t* __restrict__ D, int B, int Hs, int Ws,
     int H, int W, float* __restrict__ input, float* __restrict__ target, uint8_t* __restrict__ mask,
     unsigned long long* __restrict__ valid_count, const AugParams* __restrict__ aug, float* __restrict__ gray_part,
     int parts_per_view, int max_rows, int row_bytes) {
     SDN_PDL_ENTRY();
-    extern __shared__ __align__(16) uint8_t sm[];
-    const int n = blockIdx.y;
+    // A CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (sample, row block, column block) grid;
+    // with a second shared-memory buffer the source rows of tile t+1 stream in (cp.async, every 16-byte chunk in
+    // flight at once) while tile t is computed.  Measured: the kernel is bound by its compute phase (latency of
+    // the conversion / interpolation chains), not by staging - one persistent 512-thread CTA per SM with two
+    // buffers ran 0.96 ms where three independent 256-thread CTAs per SM (one tile each, launched that way by
+    // the host: gridDim.x == number of tiles, one buffer) run 0.68 ms - so occupancy wins over pipelining here.
+    extern __shared__ __align__(16) uint8_t sm_all[];
     const int xblocks = (W + 127) / 128;
-    const int xb = blockIdx.x % xblocks;
-    const int yb = blockIdx.x / xblocks;
+    const int tiles_per_sample = parts_per_view;                 // == xblocks * yblocks
+    const int num_tiles = B * tiles_per_sample;
+    const size_t buf_bytes = (size_t)3 * max_rows * row_bytes;
     const float sy = (float)Hs / (float)H;
     const float sx = (float)Ws / (float)W;
     const float wscale = (float)((double)W / (double)Ws);
     const size_t src_img = (size_t)Hs * Ws * 3;
-    const uint8_t* srcs[3] = {L + (size_t)n * src_img, R + (size_t)n * src_img, D + (size_t)n * src_img};
     const size_t plane = (size_t)H * W;
+    const size_t pitch = (size_t)Ws * 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // source footprint of this block
-    const int ox0 = xb * 128, ox1 = min(ox0 + 127, W - 1);
-    const int oy0 = yb * PRE_ROWS, oy1 = min(oy0 + PRE_ROWS - 1, H - 1);
-    int a0, a1, b0, b1;
-    float t0, t1;
-    bilinear_src(sx, ox0, Ws, W, a0, a1, t0, t1);
-    bilinear_src(sx, ox1, Ws, W, b0, b1, t0, t1);
-    const int col_first = a0, col_last = b1;
-    bilinear_src(sy, oy0, Hs, H, a0, a1, t0, t1);
-    bilinear_src(sy, oy1, Hs, H, b0, b1, t0, t1);
-    const int row_first = a0, row_last = b1;
-    const int nrows = row_last - row_first + 1;
-    const int byte0 = (col_first * 3) & ~15;                       // 16-byte aligned inside the row
-    const int byte1 = min(((col_last + 1) * 3 + 15) & ~15, Ws * 3);
-    const int chunks = (byte1 - byte0) >> 4;
-    {
-        // one warp per (image, source row) line, lanes over its 16-byte chunks: no div / mod per chunk and
-        // up to four independent 128-bit loads in flight per thread
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const size_t pitch = (size_t)Ws * 3;
-        for (int line = warp; line < 3 * nrows; line += 8) {
-            const int im = line >= 2 * nrows ? 2 : (line >= nrows ? 1 : 0);
-            const int rr = line - im * nrows;
-            const uint4* src = reinterpret_cast<const uint4*>(srcs[im] + (size_t)(row_first + rr) * pitch + byte0);
+    struct Foot { int n, part, ox0, oy0, row_first, nrows, byte0, chunks; };
+    auto footprint = [&](int t) {
+        Foot f;
+        f.n = t / tiles_per_sample;
+        f.part = t - f.n * tiles_per_sample;
+        const int xb = f.part % xblocks, yb = f.part / xblocks;
+        f.ox0 = xb * 128;
+        f.oy0 = yb * PRE_ROWS;
+        const int ox1 = min(f.ox0 + 127, W - 1), oy1 = min(f.oy0 + PRE_ROWS - 1, H - 1);
+        int a0, a1, b0, b1;
+        float t0, t1;
+        bilinear_src(sx, f.ox0, Ws, W, a0, a1, t0, t1);
+        bilinear_src(sx, ox1, Ws, W, b0, b1, t0, t1);
+        const int col_first = a0, col_last = b1;
+        bilinear_src(sy, f.oy0, Hs, H, a0, a1, t0, t1);
+        bilinear_src(sy, oy1, Hs, H, b0, b1, t0, t1);
+        f.row_first = a0;
+        f.nrows = b1 - a0 + 1;
+        f.byte0 = (col_first * 3) & ~15;                       // 16-byte aligned inside the row
+        const int byte1 = min(((col_last + 1) * 3 + 15) & ~15, Ws * 3);
+        f.chunks = (byte1 - f.byte0) >> 4;
+        return f;
+    };
+    // one warp per (image, source row) line, lanes over its 16-byte chunks
+    auto stage = [&](const Foot& f, uint8_t* sm) {
+        for (int line = warp; line < 3 * f.nrows; line += PRE_THREADS / 32) {
+            const int im = line >= 2 * f.nrows ? 2 : (line >= f.nrows ? 1 : 0);
+            const int rr = line - im * f.nrows;
+            const uint8_t* base = (im == 0 ? L : (im == 1 ? R : D)) + (size_t)f.n * src_img;
+            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(f.row_first + rr) * pitch + f.byte0);
             uint4* dst = reinterpret_cast<uint4*>(sm + (size_t)(im * max_rows + rr) * row_bytes);
-            uint4 v[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int ck = lane + 32 * t;
-                if (ck < chunks) v[t] = __ldg(src + ck);
+            for (int ck = lane; ck < f.chunks; ck += 32) {
+                const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + ck));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + ck) : "memory");
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int ck = lane + 32 * t;
-                if (ck < chunks) dst[ck] = v[t];
-            }
-            for (int ck = lane + 128; ck < chunks; ck += 32) dst[ck] = __ldg(src + ck);   // wider-than-usual rows
         }
-    }
-    __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
-    const int x = ox0 + (threadIdx.x & 127);
-    float gsumL = 0.f, gsumR = 0.f;
-    unsigned int cnt = 0;
-    float fbL = 1.f, fbR = 1.f;
-    if (aug != nullptr) { fbL = aug[2 * n].brightness; fbR = aug[2 * n + 1].brightness; }
-    if (x < W) {
-        int x0, x1;
-        float w0, w1;
-        bilinear_src(sx, x, Ws, W, x0, x1, w0, w1);
-        const int c0 = x0 * 3 - byte0, c1 = x1 * 3 - byte0;
-        for (int yy = (threadIdx.x >> 7); yy < PRE_ROWS; yy += 2) {
-            const int y = oy0 + yy;
-            if (y >= H) break;
+    __shared__ float redL[PRE_THREADS / 32], redR[PRE_THREADS / 32];
+    __shared__ unsigned int redC[PRE_THREADS / 32];
+    __shared__ int s_y0[PRE_ROWS], s_y1[PRE_ROWS];       // vertical taps of the tile's rows: once per tile, not per thread
+    __shared__ float s_h0[PRE_ROWS], s_h1[PRE_ROWS];
+    int t = blockIdx.x;
+    if (t >= num_tiles) return;
+    Foot cur = footprint(t);
+    stage(cur, sm_all);
+    int buf = 0;
+    for (; t < num_tiles; t += gridDim.x) {
+        uint8_t* sm = sm_all + (size_t)buf * buf_bytes;
+        const int tn = t + gridDim.x;
+        Foot nxt = cur;
+        if (tn < num_tiles) {
+            nxt = footprint(tn);
+            stage(nxt, sm_all + (size_t)(buf ^ 1) * buf_bytes);      // (that buffer was released by the barrier below)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        if (threadIdx.x < PRE_ROWS) {
             int y0, y1;
             float h0, h1;
-            bilinear_src(sy, y, Hs, H, y0, y1, h0, h1);
-            const size_t opix = (size_t)y * W + x;
-            float rgb[2][3];
+            bilinear_src(sy, min(cur.oy0 + (int)threadIdx.x, H - 1), Hs, H, y0, y1, h0, h1);
+            s_y0[threadIdx.x] = y0 - cur.row_first; s_y1[threadIdx.x] = y1 - cur.row_first;
+            s_h0[threadIdx.x] = h0; s_h1[threadIdx.x] = h1;
+        }
+        __syncthreads();
+
+        const int n = cur.n, byte0 = cur.byte0;
+        float* const in_n = input + (size_t)n * 6 * plane;
+        float* const tg_n = target + (size_t)n * plane;
+        uint8_t* const mk_n = mask + (size_t)n * plane;
+        const int x = cur.ox0 + (threadIdx.x & 127);
+        float gsumL = 0.f, gsumR = 0.f;
+        unsigned int cnt = 0;
+        float fbL = 1.f, fbR = 1.f;
+        if (aug != nullptr) { fbL = aug[2 * n].brightness; fbR = aug[2 * n + 1].brightness; }
+        if (x < W) {
+            int x0, x1;
+            float w0, w1;
+            bilinear_src(sx, x, Ws, W, x0, x1, w0, w1);
+            const int c0 = x0 * 3 - byte0, c1 = x1 * 3 - byte0;
+            for (int yy = (threadIdx.x >> 7); yy < PRE_ROWS; yy += PRE_THREADS / 128) {
+                const int y = cur.oy0 + yy;
+                if (y >= H) break;
+                const int y0 = s_y0[yy], y1 = s_y1[yy];
+                const float h0 = s_h0[yy], h1 = s_h1[yy];
+                const int opix = y * W + x;
+                // A tap whose weight is exactly 0 (integer scale ratios: 960 -> 320 samples column 3x+1 with
+                // w1 = 0) contributes fma(w0, a, 0 * b) = the same bits for ANY finite b: reuse the other tap
+                // instead of fetching and converting it.  Same for the vertical pair.
+                const bool skip_x = w1 == 0.f, skip_y = h1 == 0.f;
+                float rgb[2][3];
 #pragma unroll
-            for (int im = 0; im < 2; ++im) {
-                const uint8_t* r0 = sm + (size_t)(im * max_rows + (y0 - row_first)) * row_bytes;
-                const uint8_t* r1 = sm + (size_t)(im * max_rows + (y1 - row_first)) * row_bytes;
+                for (int im = 0; im < 2; ++im) {
+                    const uint8_t* r0 = sm + (im * max_rows + y0) * row_bytes;
+                    const uint8_t* r1 = sm + (im * max_rows + y1) * row_bytes;
+                    const uint32_t p00 = load_rgb24(r0 + c0);
+                    const uint32_t p01 = skip_x ? p00 : load_rgb24(r0 + c1);
+                    const uint32_t p10 = skip_y ? p00 : load_rgb24(r1 + c0);
+                    const uint32_t p11 = skip_y ? p01 : (skip_x ? p10 : load_rgb24(r1 + c1));
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float a = u8_over_255(r0[c0 + c]);
-                    const float b = u8_over_255(r0[c1 + c]);
-                    const float cc = u8_over_255(r1[c0 + c]);
-                    const float e = u8_over_255(r1[c1 + c]);
-                    rgb[im][c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
-                    input[((size_t)n * 6 + im * 3 + c) * plane + opix] = rgb[im][c];
+                    for (int c = 0; c < 3; ++c) {
+                        const float a = u8_over_255((uint8_t)(p00 >> (8 * c)));
+                        const float b = skip_x ? a : u8_over_255((uint8_t)(p01 >> (8 * c)));
+                        const float cc = skip_y ? a : u8_over_255((uint8_t)(p10 >> (8 * c)));
+                        const float e = skip_y ? b : (skip_x ? cc : u8_over_255((uint8_t)(p11 >> (8 * c))));
+                        rgb[im][c] = bilerp<FOURTERM>(a, b, cc, e, w0, w1, h0, h1);
+                        in_n[(size_t)(im * 3 + c) * plane + opix] = rgb[im][c];
+                    }
+                }
+                const uint8_t* d0 = sm + (2 * max_rows + y0) * row_bytes;
+                const uint8_t* d1 = sm + (2 * max_rows + y1) * row_bytes;
+                float dv[4];
+                dv[0] = decode_rgb24(load_rgb24(d0 + c0));
+                dv[1] = skip_x ? dv[0] : decode_rgb24(load_rgb24(d0 + c1));
+                dv[2] = skip_y ? dv[0] : decode_rgb24(load_rgb24(d1 + c0));
+                dv[3] = skip_y ? dv[1] : (skip_x ? dv[2] : decode_rgb24(load_rgb24(d1 + c1)));
+                const float tv = __fmul_rn(bilerp<FOURTERM>(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
+                tg_n[opix] = tv;
+                const bool valid = tv > 0.f;
+                mk_n[opix] = valid ? 1 : 0;
+                cnt += (valid && isfinite(tv)) ? 1u : 0u;
+                if (aug != nullptr) {
+                    gsumL += gray_of(blend(rgb[0][0], 0.f, fbL, 1.f - fbL), blend(rgb[0][1], 0.f, fbL, 1.f - fbL),
+                                     blend(rgb[0][2], 0.f, fbL, 1.f - fbL));
+                    gsumR += gray_of(blend(rgb[1][0], 0.f, fbR, 1.f - fbR), blend(rgb[1][1], 0.f, fbR, 1.f - fbR),
+                                     blend(rgb[1][2], 0.f, fbR, 1.f - fbR));
                 }
             }
-            const uint8_t* d0 = sm + (size_t)(2 * max_rows + (y0 - row_first)) * row_bytes;
-            const uint8_t* d1 = sm + (size_t)(2 * max_rows + (y1 - row_first)) * row_bytes;
-            const uint8_t* taps[4] = {d0 + c0, d0 + c1, d1 + c0, d1 + c1};
-            float dv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float r = (float)taps[k][0], g = (float)taps[k][1], b = (float)taps[k][2];
-                const float s = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(r, 255.f), 255.f), __fmul_rn(g, 255.f)), b);
-                dv[k] = __fdiv_rn(s, 1000.f);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            gsumL += __shfl_xor_sync(0xffffffffu, gsumL, o);
+            gsumR += __shfl_xor_sync(0xffffffffu, gsumR, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (lane == 0) { redL[warp] = gsumL; redR[warp] = gsumR; redC[warp] = cnt; }
+        __syncthreads();      // also: every thread is done reading this tile's buffer
+        if (threadIdx.x == 0) {
+            if (gray_part != nullptr) {
+                float a = 0.f, b = 0.f;
+                for (int w8 = 0; w8 < PRE_THREADS / 32; ++w8) { a += redL[w8]; b += redR[w8]; }
+                gray_part[(size_t)(2 * n) * parts_per_view + cur.part] = a;
+                gray_part[(size_t)(2 * n + 1) * parts_per_view + cur.part] = b;
             }
-            const float t = __fmul_rn(bilerp<FOURTERM>(dv[0], dv[1], dv[2], dv[3], w0, w1, h0, h1), wscale);
-            target[(size_t)n * plane + opix] = t;
-            const bool valid = t > 0.f;
-            mask[(size_t)n * plane + opix] = valid ? 1 : 0;
-            cnt += (valid && isfinite(t)) ? 1u : 0u;
-            if (aug != nullptr) {
-                gsumL += gray_of(blend(rgb[0][0], 0.f, fbL, 1.f - fbL), blend(rgb[0][1], 0.f, fbL, 1.f - fbL),
-                                 blend(rgb[0][2], 0.f, fbL, 1.f - fbL));
-                gsumR += gray_of(blend(rgb[1][0], 0.f, fbR, 1.f - fbR), blend(rgb[1][1], 0.f, fbR, 1.f - fbR),
-                                 blend(rgb[1][2], 0.f, fbR, 1.f - fbR));
+            if (valid_count != nullptr) {
+                unsigned int c = 0;
+                for (int w8 = 0; w8 < PRE_THREADS / 32; ++w8) c += redC[w8];
+                if (c) atomicAdd(valid_count, (unsigned long long)c);
             }
         }
-    }
-    __shared__ float redL[8], redR[8];
-    __shared__ unsigned int redC[8];
-    for (int o = 16; o > 0; o >>= 1) {
-        gsumL += __shfl_xor_sync(0xffffffffu, gsumL, o);
-        gsumR += __shfl_xor_sync(0xffffffffu, gsumR, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    if ((threadIdx.x & 31) == 0) { redL[threadIdx.x >> 5] = gsumL; redR[threadIdx.x >> 5] = gsumR; redC[threadIdx.x >> 5] = cnt; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (gray_part != nullptr) {
-            float a = 0.f, b = 0.f;
-            for (int w8 = 0; w8 < 8; ++w8) { a += redL[w8]; b += redR[w8]; }
-            gray_part[(size_t)(2 * n) * parts_per_view + blockIdx.x] = a;
-            gray_part[(size_t)(2 * n + 1) * parts_per_view + blockIdx.x] = b;
-        }
-        if (valid_count != nullptr) {
-            unsigned int c = 0;
-            for (int w8 = 0; w8 < 8; ++w8) c += redC[w8];
-            if (c) atomicAdd(valid_count, (unsigned long long)c);
-        }
+        cur = nxt;
+        buf ^= 1;
     }
 }
 
