@@ -222,6 +222,7 @@ struct sdn_ctx {
     float* gray_part = nullptr;
     float* blur_tmp = nullptr;
     float* aug_stage = nullptr;   // device copy of pinned-host augmentation parameters (2*maxB structs)
+    float* view_mean = nullptr;   // per-view gray mean (2*maxB floats)
     size_t blur_tmp_elems = 0;
     const float* params[SDN_NUM_PARAMS] = {};
     float* grads[SDN_NUM_PARAMS] = {};
@@ -921,6 +922,7 @@ static int plan_and_alloc(sdn_ctx* c) {
         c->blur_tmp_elems = (size_t)2 * B * 3 * c->H * c->W;
         carve(cur, c->blur_tmp_elems * sizeof(float), (void**)&c->blur_tmp);
         carve(cur, (size_t)2 * B * sizeof(AugParams), (void**)&c->aug_stage);
+        carve(cur, (size_t)2 * B * sizeof(float), (void**)&c->view_mean);
         if (pass == 0) {
             c->ws_bytes = (size_t)(cur - (uint8_t*)nullptr) + 4096;
             CUDA_OK(cudaMalloc((void**)&c->ws, c->ws_bytes));
@@ -1387,6 +1389,28 @@ static int backward_prologue(sdn_ctx* c, int accumulate, cudaStream_t st) {
     return 0;
 }
 
+// Photometric chain + blur + noise in place on input[B,6,H,W] (dataset.py:248-270), after a kernel that left the
+// per-tile gray partial sums in gray_part.
+static int run_augment(sdn_ctx* c, float* input, int B, const AugParams* aug, float* gray_part, float* blur_tmp, int parts,
+                       cudaStream_t st) {
+    const int H = c->H, W = c->W;
+    ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
+    if (((long long)H * W) % 4 == 0) {
+        launch_k(view_mean_kernel, (2 * B * 32 + 255) / 256, 256, 0, st, (const float*)gray_part, parts, 2 * B,
+                 1.0 / ((double)H * (double)W), c->view_mean);
+        launch_k(augment_point4_kernel, dim3((H * W / 4 + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug,
+                 (const float*)c->view_mean, blur_tmp);
+        c->launches += 2;
+    } else {
+        launch_k(augment_point_kernel, dim3((H * W + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug, gray_part, parts, blur_tmp);
+        ++c->launches;
+    }
+    launch_k(blur_noise_kernel<5>, dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st, input, B, H, W, aug, blur_tmp);
+    ++c->launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* right, const uint8_t* disparity, int B,
                             int Hs, int Ws, const AugParams* aug, float* input, float* target, uint8_t* mask,
                             unsigned long long* valid_count, unsigned flags, float* gray_part, float* blur_tmp,
@@ -1424,15 +1448,7 @@ static int preprocess_chunk(sdn_ctx* c, const uint8_t* left, const uint8_t* righ
                                                                     aug ? gray_part : nullptr, parts);
     ++c->launches;
     }
-    if (aug != nullptr) {
-        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
-        launch_k(augment_point_kernel, dim3((H * W + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug, gray_part, parts,
-                                                                              blur_tmp);
-        ++c->launches;
-        launch_k(blur_noise_kernel<5>, dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st, input, B, H, W, aug,
-                                                                                              blur_tmp);
-        ++c->launches;
-    }
+    if (aug != nullptr) SDN_OK(run_augment(c, input, B, aug, gray_part, blur_tmp, parts, st));
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1888,13 +1904,7 @@ int sdn_preprocess_cached(sdn_ctx* c, const uint8_t* left, const uint8_t* right,
                  W, input, target, mask, valid_count, aug, aug ? c->gray_part : nullptr, parts);
         ++c->launches;
     }
-    if (aug != nullptr) {
-        ProfScope ps2(c, st, "pre_augment", 0, 0.0, (double)B * H * W * 6 * 4 * 2);
-        launch_k(augment_point_kernel, dim3((H * W + 255) / 256, 2 * B), 256, 0, st, input, B, H, W, aug, c->gray_part, parts, c->blur_tmp);
-        ++c->launches;
-        launch_k(blur_noise_kernel<5>, dim3((W + 31) / 32, (H + 7) / 8, 2 * B), dim3(32, 8), 0, st, input, B, H, W, aug, c->blur_tmp);
-        ++c->launches;
-    }
+    if (aug != nullptr) SDN_OK(run_augment(c, input, B, aug, c->gray_part, c->blur_tmp, parts, st));
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -560,6 +560,91 @@ __global__ void __launch_bounds__(256) augment_point_kernel(float* __restrict__ 
     for (int c = 0; c < 3; ++c) base[c * plane + pix] = fminf(fmaxf(v[c], 0.f), 1.f);
 }
 
+// four standard normals per Philox call (two Box-Muller pairs, no output wasted)
+__device__ __forceinline__ void normal4(uint32_t seed, uint32_t view, uint32_t idx, uint32_t stream, float (&z)[4]) {
+    uint32_t r[4];
+    philox4x32_10(idx, view, 0x5DEECE66u + stream, 0x2545F491u, seed, 0xB5297A4Du, r);
+    const float u0 = ((float)(r[0] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u1 = ((float)(r[1] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u2 = ((float)(r[2] >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float u3 = ((float)(r[3] >> 8) + 0.5f) * (1.f / 16777216.f);
+#ifdef SDN_AUG_PRECISE
+    const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+#else
+    const float ra = __fsqrt_rn(-2.f * __logf(u0)), rb = __fsqrt_rn(-2.f * __logf(u2));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u1, &s0, &c0);
+    __sincosf(6.283185307179586f * u3, &s1, &c1);
+#endif
+    z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
+}
+
+// Per-view mean of the brightness-adjusted gray image (adjust_contrast's blend target), ONCE per view: one warp
+// sums the per-tile partials in a fixed order in fp64 (deterministic).  Every 256-pixel block of the point kernel
+// used to redo this reduction behind a barrier, which cost more than the block's own arithmetic.
+__global__ void __launch_bounds__(256) view_mean_kernel(const float* __restrict__ gray_part, int parts_per_view, int views,
+                                                        double inv_pixels, float* __restrict__ view_mean) {
+    SDN_PDL_ENTRY();
+    const int view = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (view >= views) return;
+    double s = 0.0;
+    for (int i = lane; i < parts_per_view; i += 32) s += (double)gray_part[(size_t)view * parts_per_view + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) view_mean[view] = (float)(s * inv_pixels);
+}
+
+// Same chain as augment_point_kernel, FOUR pixels per thread: 128-bit loads / stores of each colour plane and three
+// Philox calls for the quad's twelve normals (instead of four calls with a quarter of their output discarded).
+// grid = (ceil(H*W / 1024), 2*B); needs H*W % 4 == 0 (16-byte aligned planes).
+__global__ void __launch_bounds__(256) augment_point4_kernel(float* __restrict__ input, int B, int H, int W,
+                                                             const AugParams* __restrict__ aug,
+                                                             const float* __restrict__ view_mean,
+                                                             float* __restrict__ blur_tmp) {
+    SDN_PDL_ENTRY();
+    const int view = blockIdx.y;
+    const AugParams a = aug[view];
+    const float mean = __ldg(view_mean + view);
+    const size_t plane = (size_t)H * W;
+    const size_t quad = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (quad * 4 >= plane) return;
+    float* base = input + ((size_t)(view >> 1) * 6 + (view & 1) * 3) * plane;
+    float4 ch[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ch[c] = reinterpret_cast<const float4*>(base + c * plane)[quad];
+    float px[4][3] = {{ch[0].x, ch[1].x, ch[2].x}, {ch[0].y, ch[1].y, ch[2].y}, {ch[0].z, ch[1].z, ch[2].z}, {ch[0].w, ch[1].w, ch[2].w}};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) augment_pixel(px[j], a, mean);
+    float* dst = base;
+    if (a.blur_sigma > 0.f) {
+        dst = blur_tmp + (size_t)view * 3 * plane;      // post-gamma values: blur_noise_kernel finishes the view
+    } else {
+        if (a.noise_std > 0.f) {
+            float z[12];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float z4[4];
+                normal4(a.noise_seed, (uint32_t)view, (uint32_t)quad, (uint32_t)k, z4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) z[4 * k + i] = z4[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) px[j][c] = fmaf(z[3 * j + c], a.noise_std, px[j][c]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) px[j][c] = fminf(fmaxf(px[j][c], 0.f), 1.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        reinterpret_cast<float4*>(dst + c * plane)[quad] = make_float4(px[0][c], px[1][c], px[2][c], px[3][c]);
+}
+
 // 5x5 Gaussian (outer product of the normalised 1-D kernel, reflect padding,
 // torchvision gaussian_blur) + noise + clamp, only for views with blur_sigma > 0.
 // grid = (ceil(W/32), ceil(H/8), 2*B), block = (32, 8).
