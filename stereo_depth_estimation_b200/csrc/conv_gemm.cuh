@@ -144,6 +144,18 @@ struct CgCfg {
 // and step between 8-row groups by any stride.  ONE (TH+2) x (TW+2) box per (source, channel
 // block) then serves all NINE taps: tap (dy, dx) starts (dy*(TW+2) + dx) rows into the box and
 // strides (TW+2) rows between the 8-pixel image-row segments.  L2->SM rows per tile: 180 instead of 432.
+//
+// HALO = 3 ("super-pixel", 32-channel sources and 32 output channels, i.e. the level-1 convs): with N = 32 a
+// tcgen05.mma costs 42 cycles for 32 columns - the A operand is re-read from shared memory for every tap - so these
+// layers run at a third of the pipe.  Two horizontally adjacent pixels are ONE 64-channel super-pixel of the same
+// NHWC memory ([B,H,W,32] == [B,H,W/2,64]), so the kernel sees a (W/2) x H image with 64 input and 64 output
+// "channels" (output pixel pair x 32).  Per vertical tap the 3x3 conv becomes: the centre super-pixel with a dense
+// 64 x 64 weight block (all four pixel pairings are valid taps dx = p_in - p_out), the left neighbour with only its
+// SECOND pixel feeding the FIRST output pixel (K = 32, N = 32, columns 0-31) and the right neighbour with only its
+// first pixel feeding the second output pixel (K = 32, N = 32, columns 32-63).  24 MMAs per 256 pixels instead of
+// 36, a third less A traffic, and one barrier handshake per 256 pixels instead of two.  Same box9 addressing: one
+// (TH+2) x (TW+2) super-pixel box per source, 128-byte rows.  Weights: [unit][dy][128 rows][64 k], rows 0-63 centre,
+// 64-95 left, 96-127 right (pack modes 11 / 12).
 template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0>
 __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL>;
@@ -219,7 +231,14 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             int s = 0;
             uint32_t ph = 0;
             int dbg_it = 0;
-            if (bres && ptx::elect_one()) {
+            if (HALO == 3) {
+                if (ptx::elect_one()) {
+                    // [unit][dy] slabs of 128 rows x 128 bytes (centre 64, left 32, right 32 rows)
+                    const int slabs = p.kblocks_total * 3;
+                    ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(slabs) * 128 * 128);
+                    for (int u = 0; u < slabs; ++u) ptx::tma_load_2d(b_res + u * 128 * 128, &p.b_map, bres_bar, 0, u * 128);
+                }
+            } else if (bres && ptx::elect_one()) {
                 // every k-block's weight slabs, once: [unit][dy][BLOCK_N][KB] ([unit][dy][dx].. for box9)
                 const int slabs = p.kblocks_total * (HALO == 2 ? 3 : 1);   // 3-block TMA boxes
                 ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(slabs) * 3 * Cfg::B_BYTES);
@@ -239,7 +258,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                     for (int cb = 0; cb < seg.cblocks; ++cb) {
                         uint8_t* a_dst = stage_base + s * stage_bytes + sub * unit_bytes;
                         uint8_t* b_dst = a_dst + a_bytes;
-                        if (HALO == 2) {
+                        if (HALO == 2 || HALO == 3) {
                             const uint32_t a_box = uint32_t((p.TW + 2) * (p.TH + 2) * SWA);
                             const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
                             if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
@@ -338,6 +357,36 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                                         tmem_d, a0 + uint64_t(((tap / 3) * ROW_PITCH + (tap % 3) * SWA) / 16 + 2 * k),
                                         b0 + uint64_t(tap * Cfg::B_BYTES / 16 + 2 * k), IDESC,
                                         (tap | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);
+                            }
+                        }
+                    } else if (HALO == 3) {
+                        constexpr uint32_t ROW_PITCH = 10 * 128;   // box row = TW + 2 = 10 super-pixels of 128 bytes
+                        constexpr uint32_t IDESC32 = ptx::make_idesc_bf16(128, 32, 0, 0);
+                        const uint32_t lead = leader ? 1u : 0u;
+                        for (int j = 0; j < ups; ++j) {
+                            const uint64_t a0 = ptx::make_smem_desc(st_addr + j * unit_bytes, 16, ROW_PITCH, 2u);
+                            const uint64_t b0 = ptx::make_smem_desc(b_res_addr + (kb + j) * 3 * 128 * 128, 16, 1024, 2u);
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const uint32_t first = (dy != 0 || (kb | j) != 0) ? 1u : 0u;
+                                // centre super-pixel: K = 64, N = 64 (all four pixel pairings)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::tc_mma_bf16_pred(tmem_d, a0 + uint64_t((dy * ROW_PITCH + 128) / 16 + 2 * k),
+                                                          b0 + uint64_t(dy * (128 * 128 / 16) + 2 * k), IDESC,
+                                                          k != 0 ? 1u : first, lead);
+                                // left neighbour: its second pixel (bytes 64..127) -> first output pixel (columns 0..31)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+                                    ptx::tc_mma_bf16_pred(tmem_d, a0 + uint64_t((dy * ROW_PITCH + 64) / 16 + 2 * k),
+                                                          b0 + uint64_t(dy * (128 * 128 / 16) + (64 * 128 + 64) / 16 + 2 * k),
+                                                          IDESC32, 1u, lead);
+                                // right neighbour: its first pixel (bytes 0..63) -> second output pixel (columns 32..63)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+                                    ptx::tc_mma_bf16_pred(tmem_d + 32, a0 + uint64_t((dy * ROW_PITCH + 2 * 128) / 16 + 2 * k),
+                                                          b0 + uint64_t(dy * (128 * 128 / 16) + (96 * 128) / 16 + 2 * k),
+                                                          IDESC32, 1u, lead);
                             }
                         }
                     } else if (HALO == 1) {

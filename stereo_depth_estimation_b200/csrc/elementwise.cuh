@@ -99,6 +99,28 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ w, int mod
             v = w[(co * Ci + cc % Ci) * 9 + dy * 3 + cc / Ci];
             if (oscale != nullptr) v *= oscale[co];
         }
+    } else if (mode == 11 || mode == 12) {
+        // super-pixel layout (conv_gemm HALO = 3; Cout == 32, 32-channel sources): dst[unit][dy][row 0..127][k 0..63]
+        //   rows   0..63 : centre  (output pixel po = row >> 5, channel = row & 31; k: input pixel pi = k >> 5, c = k & 31,
+        //                           horizontal tap dx = pi - po + 1)
+        //   rows  64..95 : left neighbour, only its second pixel (k >= 32) feeds output pixel 0 (dx = 0)
+        //   rows 96..127 : right neighbour, only its first pixel (k < 32) feeds output pixel 1 (dx = 2)
+        // mode 11 (forward): value = W[row_ch][unit*32 + c][dy][dx]; mode 12 (data gradient, single 32-channel
+        // source): value = W[c][row_ch][2 - dy][2 - dx]   (flipped taps, transposed channels)
+        const int k = i & 63, row = (i >> 6) & 127, slab = i >> 13, dy = slab % 3, unit = slab / 3;
+        const int pi = k >> 5, c = k & 31;
+        int och = row & 31, dx = -1;
+        if (row < 64) dx = pi - (row >> 5) + 1;
+        else if (row < 96) dx = pi == 1 ? 0 : -1;
+        else dx = pi == 0 ? 2 : -1;
+        if (dx >= 0) {
+            if (mode == 11) {
+                v = w[(och * Ci + unit * 32 + c) * 9 + dy * 3 + dx];
+                if (oscale != nullptr) v *= oscale[och];
+            } else {
+                v = w[(c * Ci + och) * 9 + (2 - dy) * 3 + (2 - dx)];
+            }
+        }
     } else if (mode == 3) {
         const int ci = i & (Ci - 1), row = i >> lCi, q = row >> lCo, co = row & (Co - 1);
         v = w[(ci * Co + co) * 4 + q];
@@ -341,17 +363,22 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                          long long* __restrict__ num_batches, float eps, float momentum,
                                          float* __restrict__ scale, float* __restrict__ shift,
-                                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int fold) {
     SDN_PDL_ENTRY();
     // one warp per channel: lanes stride over the partial rows, fixed-shape butterfly -> deterministic
+    // fold == 2: the producing kernel ran in the super-pixel view (conv_gemm HALO = 3): partial rows hold 2*C
+    // "channels" and real channel c is the sum of columns c and c + C
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c == 0 && lane == 0 && num_batches != nullptr) *num_batches += 1;
     if (c >= C) return;
+    const int Ck = C * fold;
     double s = 0.0, q = 0.0;
     for (int i = lane; i < nparts; i += 32) {
-        s += (double)partials[(size_t)i * 2 * C + c];
-        q += (double)partials[(size_t)i * 2 * C + C + c];
+        const float* row = partials + (size_t)i * 2 * Ck;
+        s += (double)row[c];
+        q += (double)row[Ck + c];
+        if (fold == 2) { s += (double)row[C + c]; q += (double)row[Ck + C + c]; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -367,6 +394,9 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int
     shift[c] = beta[c] - (float)mean * sc;
     mean_out[c] = (float)mean;
     rstd_out[c] = rstd;
+    if (C == 32) {   // duplicates for kernels that see this layer as 64 super-pixel channels
+        scale[c + 32] = sc; shift[c + 32] = shift[c]; mean_out[c + 32] = (float)mean; rstd_out[c + 32] = rstd;
+    }
     if (running_mean != nullptr) {
         const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
@@ -385,6 +415,7 @@ __global__ void bn_prepare_eval_kernel(int C, const float* __restrict__ gamma, c
     const float sc = gamma[c] * rstd;
     scale[c] = sc;
     shift[c] = beta[c] - running_mean[c] * sc;
+    if (C == 32) { scale[c + 32] = sc; shift[c + 32] = shift[c]; }   // super-pixel view (conv_gemm HALO = 3)
 }
 
 // a = relu(y*scale + shift), optionally also p = maxpool2x2(a).
@@ -589,15 +620,19 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
 // fused conv-epilogue reduction, CG_BSTATS): multiply by rstd[c] here.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                        float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate, const float* __restrict__ rstd_scale) {
+                                       float* __restrict__ dbeta, int accumulate, const float* __restrict__ rstd_scale,
+                                       int fold) {
     SDN_PDL_ENTRY();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per channel
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
+    const int Ck = C * fold;     // fold == 2: super-pixel partial rows (see bn_finalize_train_kernel)
     double s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < nparts; i += 32) {
-        s1 += (double)partials[(size_t)i * 2 * C + c];
-        s2 += (double)partials[(size_t)i * 2 * C + C + c];
+        const float* row = partials + (size_t)i * 2 * Ck;
+        s1 += (double)row[c];
+        s2 += (double)row[Ck + c];
+        if (fold == 2) { s1 += (double)row[C + c]; s2 += (double)row[Ck + C + c]; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);

@@ -189,6 +189,7 @@ struct ConvL {  // conv3x3 + BatchNorm + ReLU
     // BatchNorm-backward sums (CG_BSTATS): bn_backward skips its reduction pass and finalizes from these partials
     bool bwd_stats_fused = false;
     int bwd_stats_parts = 0;
+    int bwd_stats_fold = 1;   // 2: the producer ran in the super-pixel view (partial rows hold 2 x C columns)
 };
 struct UpL {  // ConvTranspose2d(k=2, s=2)
     int cin = 0, cout = 0, lvl_in = 0;
@@ -334,6 +335,7 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
         CUDA_OK(cudaGetLastError());
         return 0;
     }
+    if (op.halo == 3) return launch_cg_t<128, 64, 3>(c, op, st);
     if (op.halo == 2) {
         if (op.swa == 128) {
             switch (op.block_n) {
@@ -415,6 +417,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 32, 1); SDN_SMEM_ATTR(128, 64, 1); SDN_SMEM_ATTR(128, 128, 1);
     SDN_SMEM_ATTR(64, 32, 1); SDN_SMEM_ATTR(64, 64, 1);
     SDN_SMEM_ATTR(128, 32, 2); SDN_SMEM_ATTR(128, 64, 2); SDN_SMEM_ATTR(64, 32, 2); SDN_SMEM_ATTR(64, 64, 2);
+    SDN_SMEM_ATTR(128, 64, 3);
     SDN_SMEM_ATTR(128, 128, 0, 64);
 #undef SDN_SMEM_ATTR
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -498,6 +501,68 @@ struct BStatSpec {
     const Act* y;
     const float *scale, *shift, *mean;
 };
+
+// The same tensor seen as super-pixels: [B,H,W,32] == [B,H,W/2,64]
+static SrcView super_view(const SrcView& v) {
+    SrcView s = v;
+    s.C = 64; s.W = v.W / 2; s.sW = 2 * v.sW;
+    return s;
+}
+
+// conv_gemm HALO = 3 (see conv_gemm.cuh): 3x3 conv, every source 32 channels, 32 output channels, one destination.
+// The kernel runs <128, 64, 3> on the super-pixel views; bmat holds the mode-11 / mode-12 packing.
+static int build_gemm_superpixel(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews, const bf16* bmat,
+                                 const SrcView& dview, const float* bias, int flags, float* stats_partials,
+                                 const BStatSpec* bs) {
+    memset(&op.p, 0, sizeof op.p);
+    ConvGemmParams& p = op.p;
+    op.swa = 128; op.block_n = 64; op.halo = 3; op.swd64 = false;
+    const SrcView d = super_view(dview);
+    const int W = d.W, H = d.H, units = (int)aviews.size();
+    p.TW = 8; p.TH = 16; p.TN = 1;
+    p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.tiles_n = B;
+    p.img_w = W; p.img_h = H; p.img_n = B;
+    for (int i = 0; i < units; ++i) {
+        const SrcView v = super_view(aviews[i]);
+        SDN_OK(encode4(&p.a_maps[i], v.base, 64, v.W, v.H, B, v.sW, v.sH, v.sN, 64, 10, 18, 1, 128));
+        p.segs[i].map = (int8_t)i; p.segs[i].dx = 0; p.segs[i].dy = 0; p.segs[i].c0 = 0; p.segs[i].cblocks = 1;
+    }
+    for (int i = units; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    p.nsegs = units;
+    p.kblocks_total = units;
+    p.a_stage_bytes = (10 * 18 * 128 + 1023) & ~1023;
+    SDN_OK(encode2(&p.b_map, bmat, 64, units * 3 * 128, 64, 128, 128));
+    SDN_OK(encode4(&p.d_maps[0], d.base, 64, d.W, d.H, B, d.sW, d.sH, d.sN, 64, 8, 16, 1, 128));
+    for (int i = 1; i < 4; ++i) p.d_maps[i] = p.d_maps[0];
+    int ybytes = 0;
+    p.y_map = p.d_maps[0];
+    p.ybuf = 1;
+    if (bs != nullptr) {
+        const SrcView y = super_view(full_view(*bs->y));
+        SDN_OK(encode4(&p.y_map, y.base, 64, y.W, y.H, B, y.sW, y.sH, y.sN, 64, 8, 16, 1, 128));
+        flags |= CG_BSTATS;
+        stats_partials = c->stats_partials;
+        p.bs_scale = bs->scale; p.bs_shift = bs->shift; p.bs_mean = bs->mean;   // (duplicated at [32, 64) by the finalize)
+        p.ybuf = 2;
+        ybytes = 2 * p.ybuf * 128 * 64 * 2;
+    }
+    p.n_tiles = 1; p.n_per_dmap = 64; p.n_total = 64;
+    p.flags = flags | CG_BRES;
+    p.bias = bias;
+    p.stats_partials = stats_partials;
+    p.b_res_bytes = units * 3 * 128 * 128;
+    int fixed = cg_smem_halo(128, 64, 0, p.a_stage_bytes) + ybytes;
+    if (bs != nullptr && (220 * 1024 - fixed - p.b_res_bytes) / p.a_stage_bytes < 3) {
+        p.ybuf = 1; fixed -= ybytes / 2; ybytes /= 2;
+    }
+    const int budget = 220 * 1024 - fixed - p.b_res_bytes;
+    p.ups = (units <= 2 && budget / (units * p.a_stage_bytes) >= 3) ? units : 1;
+    p.stages = std::max(2, std::min(8, budget / (p.ups * p.a_stage_bytes)));
+    op.smem = fixed + p.b_res_bytes + p.stages * p.ups * p.a_stage_bytes;
+    if (op.smem > 227 * 1024) return fail("build_gemm_superpixel: shared memory %d", op.smem);
+    op.grid = std::max(1, std::min(p.tiles_x * p.tiles_y * p.tiles_n, c->num_sms));
+    return 0;
+}
 static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>& aviews,
                       const std::vector<SegSpec>& segs_in, const bf16* bmat, int n_total,
                       const std::vector<SrcView>& dviews, int n_per_dmap, const float* bias, int flags,
@@ -507,6 +572,13 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     if (aviews.empty() || aviews.size() > 4 || dviews.empty() || dviews.size() > 4 || segs.size() > CG_MAX_SEGS)
         return fail("build_gemm: bad view/segment counts");
     memset(&op.p, 0, sizeof op.p);
+    {
+        static const int sp_on = env_int("SDN_SUPERPIX", 1), box9_ok = env_int("SDN_BOX9", 1);
+        bool sp = sp_on && box9_ok && conv3x3 && dx_taps == 3 && n_total == 32 && n_per_dmap == 32 && dviews.size() == 1 &&
+                  dviews[0].C == 32 && dviews[0].W % 16 == 0 && aviews.size() <= 2 && (bs == nullptr || bs->y->C == 32);
+        for (const SrcView& v : aviews) sp = sp && v.C == 32 && v.W == dviews[0].W && v.sW == 32;
+        if (sp) return build_gemm_superpixel(c, op, B, aviews, bmat, dviews[0], bias, flags, stats_partials, bs);
+    }
     bool all64 = true;
     for (const SrcView& v : aviews) {
         if (v.C % 32 != 0) return fail("build_gemm: source channels %d not a multiple of 32", v.C);
@@ -872,8 +944,10 @@ static int plan_and_alloc(sdn_ctx* c) {
                     carve(cur, L.pool.elems(B) / 8 * sizeof(unsigned short), (void**)&L.amax);
                 }
                 const int kdim = L.first ? 288 : 9 * L.cin;   // first layer: up to 9 x 32 workspace rows (row-halo form)
-                carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wf);
-                carve(cur, (size_t)L.cout * kdim * sizeof(bf16), (void**)&L.wd);
+                // (32 -> 32 / 64 -> 32 layers may use the super-pixel packing: 3 x 128 x 64 per 32-channel source)
+                const size_t wcap = std::max((size_t)L.cout * kdim, L.cout == 32 ? (size_t)((L.cin + 31) / 32) * 3 * 128 * 64 : 0);
+                carve(cur, wcap * sizeof(bf16), (void**)&L.wf);
+                carve(cur, wcap * sizeof(bf16), (void**)&L.wd);
                 float* vecs = nullptr;
                 carve(cur, 6 * 512 * sizeof(float), (void**)&vecs);
                 L.scale = vecs; L.shift = vecs + 512; L.mean = vecs + 1024; L.rstd = vecs + 1536;
@@ -998,6 +1072,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
             if (target != nullptr) {
                 target->bwd_stats_fused = (L.dgrad.p.flags & CG_BSTATS) != 0;
                 target->bwd_stats_parts = L.dgrad.grid * (L.dgrad.block_n <= 64 ? 2 : 1);
+                target->bwd_stats_fold = L.dgrad.halo == 3 ? 2 : 1;
             }
             if (L.nsrc == 2) {
                 // the first destination is the up-conv output gradient: its per-channel column sums are the
@@ -1029,6 +1104,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
                           &bspec));
         T.bwd_stats_fused = (U.dgrad.p.flags & CG_BSTATS) != 0;
         T.bwd_stats_parts = U.dgrad.grid * (U.dgrad.block_n <= 64 ? 2 : 1);
+        T.bwd_stats_fold = 1;
         SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
     }
     c->B = B;
@@ -1089,9 +1165,13 @@ static int pack_params(sdn_ctx* c, bool training, cudaStream_t st, int part = 2)
             add(w, L.wf, fold ? L.scale : nullptr, 2, L.cout, L.cin, 64, L.cout * 64);
         } else {
             const int n = 9 * L.cin * L.cout;
-            static const int fmode[3] = {0, 5, 8}, dmode[3] = {1, 6, 9};
-            add(w, L.wf, fold ? L.scale : nullptr, fmode[(fold ? L.fprop_eval : L.fprop).halo], L.cout, L.cin, L.fprop.swa / 2, n);
-            if (training) add(w, L.wd, nullptr, dmode[L.dgrad.halo], L.cout, L.cin, L.dgrad.swa / 2, n);
+            static const int fmode[4] = {0, 5, 8, 11}, dmode[4] = {1, 6, 9, 12};
+            const GemmOp& fop = fold ? L.fprop_eval : L.fprop;
+            // super-pixel packing: [unit][dy][128 rows][64 k] per 32-channel source (see pack_value modes 11 / 12)
+            add(w, L.wf, fold ? L.scale : nullptr, fmode[fop.halo], L.cout, L.cin, fop.swa / 2,
+                fop.halo == 3 ? (L.cin / 32) * 3 * 128 * 64 : n);
+            if (training) add(w, L.wd, nullptr, dmode[L.dgrad.halo], L.cout, L.cin, L.dgrad.swa / 2,
+                              L.dgrad.halo == 3 ? 3 * 128 * 64 : n);
         }
     }
     for (int k = 0; k < 4 && part != 0; ++k) {
@@ -1220,7 +1300,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             const double count = (double)B * L.y.H * L.y.W;
             launch_k(bn_finalize_train_kernel, (L.cout * 32 + 255) / 256, 256, 0, st, 
                 c->stats_partials, op.grid * (op.block_n <= 64 ? 2 : 1), L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
-                c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd);
+                c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd, op.halo == 3 ? 2 : 1);
             ++c->launches;
         }
         SDN_OK(run_bn_relu(c, L, B, st));
@@ -1248,7 +1328,7 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
     if (L.bwd_stats_fused) {
         // the kernel that produced `ga` already reduced sum(dz) and sum(dz * (y - mean)) per CTA (CG_BSTATS)
         launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->stats_partials, L.bwd_stats_parts, C, count,
-                 L.c1, L.c2, c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)L.rstd);
+                 L.c1, L.c2, c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)L.rstd, L.bwd_stats_fold);
         ++c->launches;
     } else {
         int grid = pool ? occ_grid(c, bn_bwd_reduce_kernel<true>, items, 256) : occ_grid(c, bn_bwd_reduce_kernel<false>, items, 256);
@@ -1261,7 +1341,7 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
                                                               c->bwd_partials, B, H, W, C);
         ++c->launches;
         launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->bwd_partials, grid, C, count, L.c1, L.c2,
-                                                                c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)nullptr);
+                                                                c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)nullptr, 1);
         ++c->launches;
     }
     if (pool)
