@@ -730,8 +730,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // reference accumulates its running sums in Python doubles, train.py:345-357):
 //   [0] sum nll  [1] sum |diff|  [2] sum diff^2  [3] sum exp(0.5*logvar); the valid count is a separate u64
 // head_grads layout: [0,32) dW_d  [32] db_d  [33,65) dW_l  [65] db_l
+// Train mode (bn_scale != nullptr): d1 is the PRE-BatchNorm output y of dec1.block.3 and the kernel applies
+// scale / shift / ReLU itself - the post-activation tensor of the last conv layer has no other consumer, so it is never
+// written (one full BatchNorm+ReLU pass over a level-1 tensor less).  With bn_partials != nullptr (MODE 1, 2 with
+// backward) the kernel also reduces that layer's BatchNorm-backward sums  s1 = sum dz, q = sum dz * (y - mean),
+// dz = (z > 0) ? dA : 0,  from the gradient it has just produced: per-block rows [2 * 32] for
+// bn_bwd_finalize_kernel, so the layer's separate reduction pass disappears as well.
+constexpr int HEAD_THREADS = 384;
 template <int MODE>
-__global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, const float* __restrict__ w_d,
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const bf16* __restrict__ d1, const float* __restrict__ w_d,
                                                    const float* __restrict__ b_d, const float* __restrict__ w_l,
                                                    const float* __restrict__ b_l, float* __restrict__ disp,
                                                    float* __restrict__ logvar, const float* __restrict__ g_disp,
@@ -742,120 +749,195 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ d1, 
                                                    double* __restrict__ sums,
                                                    unsigned long long* __restrict__ count_out,
                                                    bf16* __restrict__ g_d1, float* __restrict__ head_grads,
-                                                   long long npix) {
+                                                   long long npix, const float* __restrict__ bn_scale,
+                                                   const float* __restrict__ bn_shift, const float* __restrict__ bn_mean,
+                                                   float* __restrict__ bn_partials) {
     SDN_PDL_ENTRY();
-    __shared__ float swd[32], swl[32];
-    __shared__ float red[8][72];
-    if (threadIdx.x < 32) { swd[threadIdx.x] = w_d[threadIdx.x]; swl[threadIdx.x] = w_l[threadIdx.x]; }
+    // TWO threads per pixel (an even / odd lane pair), 16 channels each: the per-channel accumulators (head weight
+    // gradients, BatchNorm-backward sums) split over the pair, which keeps the kernel out of register spills and lets
+    // two blocks share an SM; the two half dot products meet through one shuffle.
+    constexpr int NW = HEAD_THREADS / 32;
+    __shared__ float red[NW][136];
+    __shared__ float s_par[5][32];     // head weights and BatchNorm parameters (registers are for the accumulators)
+    const int half = threadIdx.x & 1, c0 = half * 16;
+    const bool bn_in = bn_scale != nullptr;
+    const bool bn_stats = MODE != 0 && bn_partials != nullptr;
+    if (threadIdx.x < 32) {
+        s_par[0][threadIdx.x] = w_d[threadIdx.x]; s_par[1][threadIdx.x] = w_l[threadIdx.x];
+        s_par[2][threadIdx.x] = bn_in ? bn_scale[threadIdx.x] : 1.f;
+        s_par[3][threadIdx.x] = bn_in ? bn_shift[threadIdx.x] : 0.f;
+        s_par[4][threadIdx.x] = bn_in ? bn_mean[threadIdx.x] : 0.f;
+    }
     __syncthreads();
+    const float *wd = s_par[0] + c0, *wl = s_par[1] + c0, *sc = s_par[2] + c0, *sh = s_par[3] + c0, *mu = s_par[4] + c0;
     const float bd = b_d[0], bl = b_l[0];
     float inv_n = 0.f;
     if (MODE == 2) {
         const unsigned long long n = n_valid[0];
         inv_n = n > 0ull ? 1.f / (float)n : 0.f;
     }
-    float acc[72];
+    // acc: [0,16) dW_d, [16,32) dW_l of this thread's channels; 32 db_d, 33 db_l, 34..38 sum nll, |diff|, diff^2,
+    // exp(.5 logvar), count (counted by the even lane only)
+    float acc[39], bs1[16], bq[16];
     if (MODE != 0) {
 #pragma unroll
-        for (int j = 0; j < 72; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 39; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { bs1[j] = 0.f; bq[j] = 0.f; }
     }
-    // One block per SM fits (the 66 weight-gradient accumulators live in registers): two warps per scheduler
-    // cannot hide a ~1 us DRAM round trip per pixel, so the NEXT pixel's operands (64 bytes of d1, target, mask)
-    // are requested before the current one is processed.
-    const long long p_first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p_step = (long long)gridDim.x * blockDim.x;
-    uint4 nxt[4];
+    // The warp stays converged for the pair shuffles: the loop runs while ANY pair of the warp has a pixel left and
+    // a pair past the end only idles (pair-local shuffle masks measured 15 % slower).
+    const unsigned pmask = 0xffffffffu;
+    const long long p_first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const long long p_step = ((long long)gridDim.x * blockDim.x) >> 1;
+    // the NEXT pixel's operands are requested before the current one is processed (a DRAM round trip per pixel
+    // cannot be hidden otherwise at this occupancy)
+    uint4 nxt[2];
     float nxt_tg = 0.f;
     uint8_t nxt_mk = 0;
     if (p_first < npix) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) nxt[v] = ldg16(d1 + p_first * 32 + v * 8);
+        nxt[0] = ldg16(d1 + p_first * 32 + c0);
+        nxt[1] = ldg16(d1 + p_first * 32 + c0 + 8);
         if (MODE == 2) { nxt_tg = __ldg(target + p_first); nxt_mk = __ldg(mask + p_first); }
     }
-    for (long long p = p_first; p < npix; p += p_step) {
-        float f[32];
-        uint4 cur[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) cur[v] = nxt[v];
+    for (long long p = p_first; __any_sync(0xffffffffu, p < npix); p += p_step) {
+        const bool active = p < npix;
+        const uint4 cur0 = nxt[0], cur1 = nxt[1];
         const float cur_tg = nxt_tg;
-        const uint8_t cur_mk = nxt_mk;
+        const uint8_t cur_mk = active ? nxt_mk : (uint8_t)0;
         if (p + p_step < npix) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) nxt[v] = ldg16(d1 + (p + p_step) * 32 + v * 8);
+            nxt[0] = ldg16(d1 + (p + p_step) * 32 + c0);
+            nxt[1] = ldg16(d1 + (p + p_step) * 32 + c0 + 8);
             if (MODE == 2) { nxt_tg = __ldg(target + p + p_step); nxt_mk = __ldg(mask + p + p_step); }
         }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        float yv[16], f[16];
+        {
             float t8[8];
-            unpack8(cur[v], t8);
+            unpack8(cur0, t8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[v * 8 + j] = t8[j];
-        }
-        float zd = bd, zl = bl;
+            for (int j = 0; j < 8; ++j) yv[j] = t8[j];
+            unpack8(cur1, t8);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { zd = fmaf(f[j], swd[j], zd); zl = fmaf(f[j], swl[j], zl); }
-        const float dsp = zd > 20.f ? zd : log1pf(expf(zd));
-        const float lv = fminf(fmaxf(zl, -6.f), 3.f);
-        if (MODE != 1) {
-            if (disp != nullptr) disp[p] = dsp;
-            if (logvar != nullptr) logvar[p] = lv;
+            for (int j = 0; j < 8; ++j) yv[8 + j] = t8[j];
         }
-        if (MODE == 0) continue;
-        float gd, gl;
-        if (MODE == 1) {
-            gd = g_disp[p];
-            gl = g_logvar != nullptr ? g_logvar[p] : 0.f;
-        } else {
-            const float tg = cur_tg;
-            const bool m = (cur_mk != 0) && isfinite(tg);
-            gd = 0.f; gl = 0.f;
-            if (m) {
-                const float diff = dsp - tg;
-                const float ad = fabsf(diff);
-                const float e = expf(-lv);
-                const float nll = ad * e + lv;
-                acc[66] += nll;
-                acc[67] += ad;
-                acc[68] = fmaf(diff, diff, acc[68]);
-                acc[69] += expf(0.5f * lv);
-                acc[70] += 1.f;
-                const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                gd = sg * e * inv_n;
-                gl = (1.f - ad * e) * inv_n;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)   // a = relu(y * scale + shift), kept in fp32 (this tensor is never stored)
+            f[j] = bn_in ? fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f) : yv[j];
+        float zd = 0.f, zl = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { zd = fmaf(f[j], wd[j], zd); zl = fmaf(f[j], wl[j], zl); }
+        // fixed summation order (channels 0-15, then 16-31, then the bias) on both lanes of the pair
+        const float zd_o = __shfl_xor_sync(pmask, zd, 1), zl_o = __shfl_xor_sync(pmask, zl, 1);
+        zd = (half ? zd_o + zd : zd + zd_o) + bd;
+        zl = (half ? zl_o + zl : zl + zl_o) + bl;
+        // the scalar part of the pixel (softplus / clamp, loss, gradient seeds) runs on the even lane only; the odd
+        // lane receives the two seeds through shuffles
+        float dzd = 0.f, dzl = 0.f;
+        if (half == 0 && active) {
+            const float dsp = zd > 20.f ? zd : log1pf(expf(zd));
+            const float lv = fminf(fmaxf(zl, -6.f), 3.f);
+            if (MODE != 1) {
+                if (disp != nullptr) disp[p] = dsp;
+                if (logvar != nullptr) logvar[p] = lv;
+            }
+            if (MODE != 0) {
+                float gd, gl;
+                if (MODE == 1) {
+                    gd = g_disp[p];
+                    gl = g_logvar != nullptr ? g_logvar[p] : 0.f;
+                } else {
+                    const float tg = cur_tg;
+                    const bool m = (cur_mk != 0) && isfinite(tg);
+                    gd = 0.f; gl = 0.f;
+                    if (m) {
+                        const float diff = dsp - tg;
+                        const float ad = fabsf(diff);
+                        const float e = expf(-lv);
+                        acc[34] += ad * e + lv;
+                        acc[35] += ad;
+                        acc[36] = fmaf(diff, diff, acc[36]);
+                        acc[37] += expf(0.5f * lv);
+                        acc[38] += 1.f;
+                        const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                        gd = sg * e * inv_n;
+                        gl = (1.f - ad * e) * inv_n;
+                    }
+                }
+                const float sig = zd > 20.f ? 1.f : 1.f / (1.f + expf(-zd));
+                dzd = gd * sig;
+                dzl = (zl >= -6.f && zl <= 3.f) ? gl : 0.f;
             }
         }
-        const float sig = zd > 20.f ? 1.f : 1.f / (1.f + expf(-zd));
-        const float dzd = gd * sig;
-        const float dzl = (zl >= -6.f && zl <= 3.f) ? gl : 0.f;
-        float o[8];
+        if (MODE == 0) continue;
+        dzd = __shfl_sync(pmask, dzd, (threadIdx.x & 31) & ~1);
+        dzl = __shfl_sync(pmask, dzl, (threadIdx.x & 31) & ~1);
+        if (!active) continue;      // (after the last shuffle of the iteration)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 2; ++v) {
+            float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(dzd, swd[v * 8 + j], dzl * swl[v * 8 + j]);
-            *reinterpret_cast<uint4*>(g_d1 + p * 32 + v * 8) = pack8(o);
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(dzd, wd[v * 8 + j], dzl * wl[v * 8 + j]);
+            const uint4 packed = pack8(o);
+            *reinterpret_cast<uint4*>(g_d1 + p * 32 + c0 + v * 8) = packed;
+            if (bn_stats) {
+                float g8[8];
+                unpack8(packed, g8);          // the bf16 values the apply pass will read back
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = v * 8 + j;
+                    const float dz = f[ch] > 0.f ? g8[j] : 0.f;      // relu(z) > 0 <=> z > 0
+                    bs1[ch] += dz;
+                    bq[ch] = fmaf(dz, yv[ch] - mu[ch], bq[ch]);
+                }
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { acc[j] = fmaf(dzd, f[j], acc[j]); acc[33 + j] = fmaf(dzl, f[j], acc[33 + j]); }
-        acc[32] += dzd;
-        acc[65] += dzl;
+        for (int j = 0; j < 16; ++j) { acc[j] = fmaf(dzd, f[j], acc[j]); acc[16 + j] = fmaf(dzl, f[j], acc[16 + j]); }
+        if (half == 0) { acc[32] += dzd; acc[33] += dzl; }
     }
     if (MODE == 0) return;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    // per-warp reduction over the 16 lanes of each parity (offsets 2..16), then the 8 warps through shared memory.
+    // red row layout: [0,32) dW_d by channel, [32,64) dW_l, 64 db_d, 65 db_l, 66..70 sums, [72,104) BatchNorm s1, [104,136) q
 #pragma unroll
-    for (int j = 0; j < 71; ++j) {
+    for (int j = 0; j < 39; ++j) {
         float v = acc[j];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[wrp][j] = v;
+        for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (j >= 32) v += __shfl_xor_sync(0xffffffffu, v, 1);      // scalars: both parities (the odd lanes hold zeros)
+        if (lane < 2) {
+            if (j < 16) red[wrp][lane * 16 + j] = v;
+            else if (j < 32) red[wrp][32 + lane * 16 + (j - 16)] = v;
+            else if (lane == 0) red[wrp][64 + (j - 32)] = v;
+        }
+    }
+    if (bn_stats) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = bs1[j], b = bq[j];
+            for (int o = 16; o > 1; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (lane < 2) { red[wrp][72 + lane * 16 + j] = a; red[wrp][104 + lane * 16 + j] = b; }
+        }
     }
     __syncthreads();
     if (threadIdx.x < 71) {
         float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-        if (threadIdx.x < 66) atomicAdd(head_grads + threadIdx.x, v);
+        for (int w = 0; w < NW; ++w) v += red[w][threadIdx.x];
+        // head_grads layout: [0,32) dW_d  [32] db_d  [33,65) dW_l  [65] db_l
+        if (threadIdx.x < 32) atomicAdd(head_grads + threadIdx.x, v);
+        else if (threadIdx.x < 64) atomicAdd(head_grads + 33 + (threadIdx.x - 32), v);
+        else if (threadIdx.x == 64) atomicAdd(head_grads + 32, v);
+        else if (threadIdx.x == 65) atomicAdd(head_grads + 65, v);
         else if (MODE == 2) {
             if (threadIdx.x < 70) atomicAdd(sums + (threadIdx.x - 66), (double)v);
             else atomicAdd(count_out, (unsigned long long)v);  // block partial < 2^24: exact
         }
+    }
+    if (bn_stats && threadIdx.x >= 128 && threadIdx.x < 192) {
+        // this block's BatchNorm-backward partial row [s1[32] | q[32]] for bn_bwd_finalize_kernel
+        const int t = threadIdx.x - 128;
+        float v = 0.f;
+        for (int w = 0; w < NW; ++w) v += red[w][72 + t];
+        bn_partials[(size_t)blockIdx.x * 64 + t] = v;
     }
 }
 

@@ -1303,15 +1303,19 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
                 c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd, op.halo == 3 ? 2 : 1);
             ++c->launches;
         }
-        SDN_OK(run_bn_relu(c, L, B, st));
+        // dec1.block.3 (the last conv layer): its activated output feeds only the two 1x1 heads, which apply
+        // scale / shift / ReLU on the fly from y (head_kernel): no BatchNorm+ReLU pass, no `a` tensor
+        if (i != 17) SDN_OK(run_bn_relu(c, L, B, st));
     }
     if (disp != nullptr) {
         const long long npix = (long long)B * H * W;
         ProfScope ps(c, st, "head_fwd", 0, 0.0, (double)npix * (64 + (logvar ? 8 : 4)));
-        launch_k(head_kernel<0>, occ_grid(c, head_kernel<0>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63],
+        const ConvL& T = c->conv[17];
+        launch_k(head_kernel<0>, occ_grid(c, head_kernel<0>, 2 * npix, HEAD_THREADS), HEAD_THREADS, 0, st, training ? T.y.p : T.a.p, c->params[62], c->params[63],
                                                               c->params[64], c->params[65], disp, logvar, nullptr,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                              nullptr, nullptr, npix);
+                                                              nullptr, nullptr, npix, training ? T.scale : nullptr,
+                                                              training ? T.shift : nullptr, training ? T.mean : nullptr, nullptr);
         ++c->launches;
         CUDA_OK(cudaGetLastError());
     }
@@ -1694,10 +1698,13 @@ int sdn_backward_begin(sdn_ctx* c, const float* g_disp, const float* g_logvar, i
     SDN_OK(backward_prologue(c, accumulate, st));
     const long long npix = (long long)c->B * c->H * c->W;
     ProfScope ps(c, st, "head_bwd", 0, 0.0, (double)npix * (64 + 8 + 64));
-    launch_k(head_kernel<1>, occ_grid(c, head_kernel<1>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+    ConvL& T = c->conv[17];
+    const int hgrid = occ_grid(c, head_kernel<1>, 2 * npix, HEAD_THREADS);
+    launch_k(head_kernel<1>, hgrid, HEAD_THREADS, 0, st, T.y.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], nullptr, nullptr, g_disp, g_logvar, nullptr,
-                                                          nullptr, nullptr, nullptr, nullptr, c->conv[17].ga.p,
-                                                          c->head_grads, npix);
+                                                          nullptr, nullptr, nullptr, nullptr, T.ga.p,
+                                                          c->head_grads, npix, T.scale, T.shift, T.mean, c->stats_partials);
+    T.bwd_stats_fused = true; T.bwd_stats_parts = hgrid; T.bwd_stats_fold = 1;
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     return head_grads_out(c, st);
@@ -1739,10 +1746,15 @@ int sdn_loss_begin(sdn_ctx* c, const float* target, const uint8_t* mask, float* 
     }
     // the gradient buffer of dec1's output doubles as scratch on the metrics-only path
     ProfScope ps(c, st, "head_loss", 0, 0.0, (double)npix * (64 + 4 + 1 + 64));
-    launch_k(head_kernel<2>, occ_grid(c, head_kernel<2>, npix, 256), 256, 0, st, c->conv[17].a.p, c->params[62], c->params[63], c->params[64],
+    ConvL& T = c->conv[17];
+    const bool train_fwd = c->have_forward_train;     // the forward just run was a training forward: d1 = y (see forward_impl)
+    const int hgrid = occ_grid(c, head_kernel<2>, 2 * npix, HEAD_THREADS);
+    launch_k(head_kernel<2>, hgrid, HEAD_THREADS, 0, st, train_fwd ? T.y.p : T.a.p, c->params[62], c->params[63], c->params[64],
                                                           c->params[65], disp, logvar, nullptr, nullptr, target, mask,
-                                                          n_norm_dev, sums4, count, c->conv[17].ga.p, c->head_grads,
-                                                          npix);
+                                                          n_norm_dev, sums4, count, T.ga.p, c->head_grads,
+                                                          npix, train_fwd ? T.scale : nullptr, train_fwd ? T.shift : nullptr,
+                                                          train_fwd ? T.mean : nullptr, with_backward ? c->stats_partials : nullptr);
+    if (with_backward) { T.bwd_stats_fused = true; T.bwd_stats_parts = hgrid; T.bwd_stats_fold = 1; }
     ++c->launches;
     CUDA_OK(cudaGetLastError());
     if (with_backward) return head_grads_out(c, st);
