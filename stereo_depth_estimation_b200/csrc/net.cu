@@ -484,6 +484,18 @@ static SrcView quad_view(const Act& u, int q) {
     return v;
 }
 
+// Row-parity i of a 2x-upsampled tensor u[B, 2h, 2w, C], seen at the low resolution with the two horizontally adjacent
+// output pixels (quadrants (i,0) and (i,1)) as ONE pixel of 2C contiguous channels: the same bytes as quad_view(u, 2i)
+// and quad_view(u, 2i+1), but in boxes with 2C-channel rows (half the TMA boxes, twice the contiguous run).
+static SrcView pair_view(const Act& u, int i) {
+    SrcView v;
+    v.base = u.p + (long long)i * u.W * u.C;
+    v.C = 2 * u.C;
+    v.W = u.W / 2; v.H = u.H / 2;
+    v.sW = 2LL * u.C; v.sH = 2LL * u.W * u.C; v.sN = (long long)u.H * u.W * u.C;
+    return v;
+}
+
 // Fill a GemmOp.  segs: list of (view index, dx, dy); every view contributes all
 // of its channels per segment.  dviews: destination views, each n_per_dmap wide.
 struct SegSpec {
@@ -1095,11 +1107,22 @@ static int prepare_batch(sdn_ctx* c, int B) {
         UpL& U = c->up[k];
         std::vector<SrcView> quads_u, quads_gu;
         for (int q = 0; q < 4; ++q) { quads_u.push_back(quad_view(U.u, q)); quads_gu.push_back(quad_view(U.gu, q)); }
+        // the GEMM columns are [quadrant q = 2i + j][co]: quadrants (i,0), (i,1) are adjacent in N and in memory
+        static const int pair_on = env_int("SDN_CONVT_PAIRS", 1);
+        std::vector<SrcView> pairs_u = {pair_view(U.u, 0), pair_view(U.u, 1)}, pairs_gu = {pair_view(U.gu, 0), pair_view(U.gu, 1)};
+        if (pair_on)
+            SDN_OK(build_gemm(c, U.fprop, B, {full_view(*U.src)}, {{0, 0, 0}}, U.wf, 4 * U.cout, pairs_u, 2 * U.cout, U.bias4,
+                              0, nullptr));
+        else
         SDN_OK(build_gemm(c, U.fprop, B, {full_view(*U.src)}, {{0, 0, 0}}, U.wf, 4 * U.cout, quads_u, U.cout, U.bias4,
                           0, nullptr));
         std::vector<SegSpec> qsegs = {{0, 0, 0}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}};
         ConvL& T = c->conv[U.src_layer];     // bottleneck.3 / dec4.3 / dec3.3 / dec2.3: not pooled
         const BStatSpec bspec{&T.y, T.scale, T.shift, T.mean};
+        if (pair_on)
+            SDN_OK(build_gemm(c, U.dgrad, B, pairs_gu, {{0, 0, 0}, {1, 0, 0}}, U.wd, U.cin, {full_view(T.ga)}, U.cin, nullptr, 0,
+                              nullptr, false, 3, &bspec));
+        else
         SDN_OK(build_gemm(c, U.dgrad, B, quads_gu, qsegs, U.wd, U.cin, {full_view(T.ga)}, U.cin, nullptr, 0, nullptr, false, 3,
                           &bspec));
         T.bwd_stats_fused = (U.dgrad.p.flags & CG_BSTATS) != 0;
