@@ -592,11 +592,12 @@ def run_b200(args):
         try:
             with open(os.path.join(ROOT, "profiles", src)) as f:
                 cap = json.load(f)
-            fam_cap = cap["families"]["forward_conv(fprop+convT_fprop)"]
+            key = "conv_fprop" if "conv_fprop" in cap["families"] else "forward_conv(fprop+convT_fprop)"
+            fam_cap = cap["families"][key]
             if b_local == 256:
                 roof["traffic"] = fam_cap["dram_bytes"] / fam_cap["launches"]
-                roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum" \
-                                         " of the 22 forward conv_gemm launches of one step = 18 conv fprop + 4 ConvTranspose2d fprop)"
+                roof["traffic_source"] = "profiles/" + src + " (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the " \
+                                         + str(fam_cap["launches"]) + " launches of family '" + key + "' in one step, per launch)"
                 roof["algorithmic_bytes_per_launch"] = fam_cap["algorithmic_bytes"] / fam_cap["launches"]
             break
         except Exception:
