@@ -28,4 +28,14 @@ model.eval()
 with torch.inference_mode():
     d, lv = model(out["input"], return_uncertainty=True)
 torch.cuda.synchronize()
-print("ok", float(d.mean()), step.read_metrics())
+# rows N3 / N4: cache-format entry and the live-view pre / post kernels
+from stereo_depth_estimation_b200 import LivePipeline
+l8 = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).to(dev)
+d16 = torch.from_numpy((rng.random((B, H, W)) * 50).astype(np.float16)).to(dev)
+pre.from_cache(l8, l8, d16, aug=sampler.sample_packed(B), count_out=count)
+live = LivePipeline(model, model_size=(W, H), ema_alpha=0.5, focal_length_px=100.0, baseline_m=0.07)
+f0 = rng.integers(0, 256, (123, 157, 3), dtype=np.uint8)
+maps = live(f0, f0)
+maps = live(f0, f0)
+torch.cuda.synchronize()
+print("ok", float(d.mean()), step.read_metrics(), float(np.nanmean(maps["depth"])))
