@@ -1317,8 +1317,9 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
             ProfScope ps(c, st, "conv_fprop", i, 2.0 * px * L.cout * 9 * L.cin, px * ((L.first ? c->x0.C : L.cin) + L.cout) * 2);
             SDN_OK(launch_cg(c, op, st));
         }
+        // (layer 17 only finalizes its statistics here: its BatchNorm+ReLU runs inside the head kernel)
         ProfScope ps(c, st, "bn_relu_pool", i, 0.0,
-                     (double)B * L.y.H * L.y.W * L.cout * 2 * (L.pooled_out ? 2.25 : 2.0));
+                     i == 17 ? 0.0 : (double)B * L.y.H * L.y.W * L.cout * 2 * (L.pooled_out ? 2.25 : 2.0));
         if (training) {
             const double count = (double)B * L.y.H * L.y.W;
             launch_k(bn_finalize_train_kernel, (L.cout * 32 + 255) / 256, 256, 0, st, 
