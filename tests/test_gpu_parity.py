@@ -771,8 +771,9 @@ def test_graphed_train_step_matches_eager(dev):
     mean_graph, mean_eager = sum(c_graph.values()) / len(c_graph), sum(c_eager.values()) / len(c_eager)
     print(f"update cosine graph-vs-eager mean {mean_graph:.4f} min {c_graph[worst]:.4f} ({worst}); "
           f"eager-vs-eager mean {mean_eager:.4f} min {min(c_eager.values()):.4f}")
-    # (two eager runs of the same steps land between 0.96 and 0.99 in their worst tensor, run to run)
-    assert mean_graph > 0.99 and c_graph[worst] > 0.9
+    # (two EAGER runs of the same seven steps agree to mean 0.985 / worst tensor 0.96-0.99, run to run: the bar for
+    # graph-vs-eager is that same neighbourhood)
+    assert mean_graph > 0.97 and mean_graph > mean_eager - 0.01 and c_graph[worst] > 0.9
     for k in pa:
         if "num_batches" in k:
             assert int(pa[k]) == int(pb[k]) == 7
