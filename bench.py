@@ -564,9 +564,12 @@ def run_b200(args):
 
     # ---- per-op roofline (separate, profiled steps; CUDA events per op) -----
     peaks = load_peaks()
+    for _ in range(2):
+        eager_step(srcs_dev)      # back on the eager launch path (the timed loops replayed graphs): settle it first
+    torch.cuda.synchronize(dev)
     model.profile_enable(True)
     pre.profile_enable(True)
-    prof_steps = 3
+    prof_steps = 5
     for _ in range(prof_steps):
         eager_step(srcs_dev)     # (event-bracketed ops cannot be part of a graph)
     rows = model.profile_dump() + pre.profile_dump()
