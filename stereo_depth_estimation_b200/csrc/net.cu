@@ -597,7 +597,6 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         if (v.C % 64 != 0) all64 = false;
     }
     op.swa = all64 ? 128 : 64;
-    const int KB = op.swa / 2;
     int bn = std::min(n_per_dmap, 256);
     // narrow destinations (dgrad of a concat input): one tile spans both, so the A operand is fetched once
     op.swd64 = false;
@@ -641,6 +640,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     op.halo = (conv3x3 && bn <= g_halo_max_n) ? 1 : 0;
     Tile t = choose_tile(W, H, B, 128);
     static const int box9_on = env_int("SDN_BOX9", 1), bres_max = env_int("SDN_BRES_MAXKB", 80) * 1024;
+    int smem_budget = 220 * 1024;
     {
         // box9: one (TH+2)x(TW+2) box per (source, channel block) feeds all nine taps; needs the whole
         // packed weight matrix resident in shared memory and 8-pixel-wide tiles
@@ -649,10 +649,26 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // (two pipeline stages of one 18x10 box must still fit next to the weights and the store staging)
         const int box9_stage = (10 * 18 * op.swa + 1023) & ~1023;
         const int box9_need = (bn <= 64 ? cg_smem_halo(op.swa, bn, 0, box9_stage) : 1 << 30) + 9 * cin_tot * bn * 2 + 2 * box9_stage;
-        if (op.halo && dx_taps == 3 && box9_on && bn == n_total && bn <= 64 && W % 8 == 0 && 9 * cin_tot * bn * 2 <= bres_max &&
-            box9_need <= 227 * 1024)
+        const bool box9_shape = op.halo && dx_taps == 3 && box9_on && bn == n_total && bn <= 64 && W % 8 == 0;
+        if (box9_shape && 9 * cin_tot * bn * 2 <= bres_max && box9_need <= 227 * 1024) {
             op.halo = 2;
+        } else if (box9_shape && op.swa == 128 && n_per_dmap == n_total && bs == nullptr) {
+            // 128 input channels -> 64 (dec2.0 forward, enc3.0 data gradient): the 147 KB weight matrix does not fit
+            // next to 128-byte-row stages, and the row-halo form re-streams it from L2 for every tile (252 KB of
+            // L2->SM traffic per 128 pixels: these two layers ran at 46 % of the pipe where their same-FLOP siblings
+            // reach 66-70 %).  With HALF k-blocks (32 channels, 64-byte swizzle rows: 11.5 KB per 18x10 box) three
+            // pipeline stages fit next to the resident weights: 46 KB per tile.
+            static const int half_on = env_int("SDN_BOX9_HALFK", 1), half_max = env_int("SDN_BOX9_HALFK_MAXKB", 150) * 1024;
+            const int stage64 = (10 * 18 * 64 + 1023) & ~1023;
+            const int need64 = cg_smem_halo(64, bn, 0, stage64) + 9 * cin_tot * bn * 2 + 3 * stage64;
+            if (half_on && 9 * cin_tot * bn * 2 <= half_max && need64 <= 226 * 1024) {
+                op.swa = 64;
+                op.halo = 2;
+                smem_budget = 226 * 1024;
+            }
+        }
     }
+    const int KB = op.swa / 2;
     if (op.halo == 2) {
         t = Tile{8, 16, 1};
         segs.clear();
@@ -734,14 +750,14 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     if (op.halo == 2) {
         const int b_total = kblocks * 9 * bn * op.swa;
         int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;
-        if (bs != nullptr && p.ybuf == 2 && (220 * 1024 - fixed - b_total) / p.a_stage_bytes < 3) {
+        if (bs != nullptr && p.ybuf == 2 && (smem_budget - fixed - b_total) / p.a_stage_bytes < 3) {
             p.ybuf = 1;            // big resident weights (64 -> 64): keep three pipeline stages instead
             fixed -= ybytes / 2;
             ybytes /= 2;
         }
         p.flags |= CG_BRES;
         p.b_res_bytes = b_total;
-        const int budget = 220 * 1024 - fixed - b_total;
+        const int budget = smem_budget - fixed - b_total;
         // every unit of a tile in one stage when at least three such stages fit
         p.ups = (kblocks <= 3 && budget / (kblocks * p.a_stage_bytes) >= 3) ? kblocks : 1;
         stages = std::max(2, std::min(8, budget / (p.ups * p.a_stage_bytes)));
