@@ -84,11 +84,13 @@ struct alignas(64) ConvGemmParams {
 #define SDN_ABLATE(flag) false
 #endif
 
-template <int SWA, int BLOCK_N, int SWD_SEL = 0>
+template <int SWA, int BLOCK_N, int SWD_SEL = 0, int NCTA = 1>
 struct CgCfg {
     static constexpr int KB = SWA / 2;  // bf16 channels per k-block
     static constexpr int A_BYTES = 128 * SWA;
-    static constexpr int B_BYTES = BLOCK_N * SWA;
+    // NCTA == 2 (CTA pair, tcgen05 cta_group::2): this CTA stages HALF of the tile's B rows
+    static constexpr int BN_LOC = BLOCK_N / NCTA;
+    static constexpr int B_BYTES = BN_LOC * SWA;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // staging / store swizzle: 64-channel blocks, except 32-channel blocks for N = 32 and for 32-channel
     // sources (so that a 64-wide tile can be split over two 32-channel destinations: dec1 dgrad)
@@ -156,13 +158,35 @@ struct CgCfg {
 // 36, a third less A traffic, and one barrier handshake per 256 pixels instead of two.  Same box9 addressing: one
 // (TH+2) x (TW+2) super-pixel box per source, 128-byte rows.  Weights: [unit][dy][128 rows][64 k], rows 0-63 centre,
 // 64-95 left, 96-127 right (pack modes 11 / 12).
-template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0>
-__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL>;
+//
+// NCTA = 2 (CTA pairs, N >= 128 tiles; HALO 0 / 1): the two CTAs of a cluster take the same tile position in two
+// consecutive image groups (tn = 2 * pair_tn + rank) and run it as ONE M = 256 tcgen05.mma.cta_group::2 per k-step:
+// each CTA loads its own A box and HALF of the weight rows, every TMA load of the pair completes on the LEADER's
+// full barrier, the leader (cluster rank 0) issues, its commits are multicast to both CTAs' barriers, and the peer's
+// epilogue warps release the accumulator stage on the leader's barrier through the cluster window.  The weight bytes
+// that cross L2 -> SM per FLOP halve: these layers were pinned at the L2 throughput cap (ncu: 10.5-11.4 TB/s of
+// lts2xbar traffic), not at the tensor pipe.
+template <bool PAIR>
+__device__ __forceinline__ void cg_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t issue) {
+    if constexpr (PAIR) ptx::tc_mma_bf16_pair_pred(tmem_d, adesc, bdesc, idesc, accumulate, issue);
+    else ptx::tc_mma_bf16_pred(tmem_d, adesc, bdesc, idesc, accumulate, issue);
+}
+template <bool PAIR>
+__device__ __forceinline__ void cg_commit(uint64_t* bar) {
+    if constexpr (PAIR) ptx::tc_commit_pair(bar);
+    else ptx::tc_commit(bar);
+}
+
+template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0, int NCTA = 1>
+__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA>;
     constexpr int KB = Cfg::KB;
+    constexpr bool PAIR = NCTA == 2;
+    static_assert(!PAIR || (HALO <= 1 && Cfg::EG == 1 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo kernels with N >= 128");
     constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
     constexpr uint32_t SBO_A = 8 * SWA;
-    constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BLOCK_N, 0, 0);
+    constexpr uint32_t IDESC = ptx::make_idesc_bf16(128 * NCTA, BLOCK_N, 0, 0);
 
     ptx::pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
@@ -191,6 +215,10 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // tile walking: a CTA pair is one worker (p.tiles_n counts PAIRS of image groups then)
+    const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const int wid = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int wstep = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int num_tiles = m_tiles * p.n_tiles;
 
@@ -201,7 +229,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 4);
+            ptx::mbar_init(&tempty_bar[a], 4 * NCTA);   // the epilogue warps of BOTH CTAs of a pair
         }
         ptx::mbar_init(bres_bar, 1);
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&ybar_all[i], 1);
@@ -214,11 +242,12 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
         if (bstats) ptx::prefetch_tmap(&p.y_map);
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
@@ -241,14 +270,19 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             } else if (bres && ptx::elect_one()) {
                 // every k-block's weight slabs, once: [unit][dy][BLOCK_N][KB] ([unit][dy][dx].. for box9)
                 const int slabs = p.kblocks_total * (HALO == 2 ? 3 : 1);   // 3-block TMA boxes
-                ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(slabs) * 3 * Cfg::B_BYTES);
-                for (int u = 0; u < slabs; ++u)
-                    ptx::tma_load_3d(b_res + u * 3 * Cfg::B_BYTES, &p.b_map, bres_bar, 0, 0, u * 3);
+                if (!PAIR || cta_rank == 0) ptx::mbar_arrive_expect_tx(bres_bar, uint32_t(NCTA * slabs) * 3 * Cfg::B_BYTES);
+                const uint32_t bres_lead = PAIR ? ptx::mapa_u32(bres_bar, 0) : 0u;
+                for (int u = 0; u < slabs; ++u) {
+                    if (PAIR) ptx::tma_load_3d_pair(b_res + u * 3 * Cfg::B_BYTES, &p.b_map, bres_lead, 0, int(cta_rank) * Cfg::BN_LOC, u * 3);
+                    else ptx::tma_load_3d(b_res + u * 3 * Cfg::B_BYTES, &p.b_map, bres_bar, 0, 0, u * 3);
+                }
             }
+            const uint32_t full_lead0 = PAIR ? ptx::mapa_u32(&full_bar[0], 0) : 0u;   // the leader's full barriers
+            const bool tx_owner = !PAIR || cta_rank == 0;
             ptx::TileWalker tw;
-            for (tw.init(blockIdx.x, gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
+            for (tw.init(wid, wstep, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid(); tw.next()) {
                 const int n_tile = tw.n_tile;
-                const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
+                const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = (PAIR ? 2 * tw.tn + int(cta_rank) : tw.tn) * p.TN;
                 int kcount = 0;
                 const int dbg_tile = dbg_it++;
                 if (lane == 0) SDN_DBG(0, dbg_tile, 0);
@@ -273,22 +307,36 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                             const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
                             if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                             if (ptx::elect_one()) {
-                                if (sub == 0)
+                                if (sub == 0 && tx_owner)
                                     ptx::mbar_arrive_expect_tx(
-                                        &full_bar[s], uint32_t(ups) * ((noa ? 0 : a_box) + (bres ? 0 : 3 * Cfg::B_BYTES)));
-                                if (!noa)
-                                    ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB,
-                                                     x0 + seg.dx, y0 - 1, n0);
-                                if (!bres)
-                                    ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
+                                        &full_bar[s], uint32_t(NCTA * ups) * ((noa ? 0 : a_box) + (bres ? 0 : 3 * Cfg::B_BYTES)));
+                                if (PAIR) {
+                                    const uint32_t fb = full_lead0 + uint32_t(s) * 8u;
+                                    ptx::tma_load_4d_pair(a_dst, &p.a_maps[seg.map], fb, seg.c0 + cb * KB, x0 + seg.dx, y0 - 1, n0);
+                                    if (!bres)
+                                        ptx::tma_load_3d_pair(b_dst, &p.b_map, fb, 0, n_tile * BLOCK_N + int(cta_rank) * Cfg::BN_LOC,
+                                                              kcount * 3);
+                                } else {
+                                    if (!noa)
+                                        ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB,
+                                                         x0 + seg.dx, y0 - 1, n0);
+                                    if (!bres)
+                                        ptx::tma_load_3d(b_dst, &p.b_map, &full_bar[s], 0, n_tile * BLOCK_N, kcount * 3);
+                                }
                             }
                         } else {
                             ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                             if (ptx::elect_one()) {
-                                ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                                ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
-                                                 y0 + seg.dy, n0);
-                                ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                                if (tx_owner) ptx::mbar_arrive_expect_tx(&full_bar[s], NCTA * Cfg::STAGE_BYTES);
+                                if (PAIR) {
+                                    const uint32_t fb = full_lead0 + uint32_t(s) * 8u;
+                                    ptx::tma_load_4d_pair(a_dst, &p.a_maps[seg.map], fb, seg.c0 + cb * KB, x0 + seg.dx, y0 + seg.dy, n0);
+                                    ptx::tma_load_2d_pair(b_dst, &p.b_map, fb, kcount * KB, n_tile * BLOCK_N + int(cta_rank) * Cfg::BN_LOC);
+                                } else {
+                                    ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 + seg.dx,
+                                                     y0 + seg.dy, n0);
+                                    ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[s], kcount * KB, n_tile * BLOCK_N);
+                                }
                             }
                         }
                         __syncwarp();
@@ -318,15 +366,16 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             uint32_t ph = 0;
             int a = dual ? mw : 0;
             uint32_t aph = 0;
-            int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            int my_tiles = wid < num_tiles ? (num_tiles - wid + wstep - 1) / wstep : 0;
             if (!dual && mw != 0) my_tiles = 0;   // the second MMA warp idles
+            if (PAIR && cta_rank != 0) my_tiles = 0;   // only the pair's leader issues
             // skip the pipeline stages of the tiles the other MMA warp consumes
             auto skip_stages = [&](int n) {
                 for (int i = 0; i < n; ++i)
                     if (++s == stages) { s = 0; ph ^= 1; }
             };
             if (NMMA == 2) skip_stages(mw * stages_per_tile);
-            if (bres) ptx::mbar_wait(bres_bar, 0);
+            if (bres && my_tiles > 0) ptx::mbar_wait(bres_bar, 0);
             const uint32_t b_res_addr = ptx::smem_u32(b_res);
             for (int it = mw; it < my_tiles; it += NMMA) {
                 if (lane == 0) SDN_DBG(1, it, 0);
@@ -401,9 +450,9 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
                             for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    ptx::tc_mma_bf16_pred(tmem_d, a0 + dy * dy_step + uint64_t(2 * k),
-                                                          b0 + uint64_t(dy * Cfg::B_BYTES / 16 + 2 * k), IDESC,
-                                                          (dy | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);
+                                    cg_mma<PAIR>(tmem_d, a0 + dy * dy_step + uint64_t(2 * k),
+                                                 b0 + uint64_t(dy * Cfg::B_BYTES / 16 + 2 * k), IDESC,
+                                                 (dy | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);
                             }
                         }
                     } else {
@@ -414,16 +463,16 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k) {
                             // +32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in the >>4 address field
-                            ptx::tc_mma_bf16_pred(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
-                                                  k != 0 ? 1u : (kb != 0 ? 1u : 0u), leader ? 1u : 0u);
+                            cg_mma<PAIR>(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), IDESC,
+                                         k != 0 ? 1u : (kb != 0 ? 1u : 0u), leader ? 1u : 0u);
                         }
                     }
-                    if (leader) ptx::tc_commit(&empty_bar[s]);
+                    if (leader) cg_commit<PAIR>(&empty_bar[s]);
                     __syncwarp();
                     if (lane == 0 && kb < 5) SDN_DBG(1, it, 2 + kb);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                if (ptx::elect_one()) ptx::tc_commit(&tfull_bar[a]);
+                if (ptx::elect_one()) cg_commit<PAIR>(&tfull_bar[a]);
                 if (lane == 0) SDN_DBG(1, it, 7);
                 if (NMMA == 2) {
                     aph ^= 1;
@@ -477,18 +526,21 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
 #pragma unroll
             for (int cbk = 0; cbk < Cfg::D_BLOCKS; ++cbk)
                 ptx::tma_load_4d(ystg + buf * Cfg::D_BYTES + cbk * Cfg::D_BLOCK_BYTES, &p.y_map, &ybar[buf],
-                                 c0 + cbk * Cfg::DCH, twy.tx * p.TW, twy.ty * p.TH, twy.tn * p.TN);
+                                 c0 + cbk * Cfg::DCH, twy.tx * p.TW, twy.ty * p.TH,
+                                 (PAIR ? 2 * twy.tn + int(cta_rank) : twy.tn) * p.TN);
         };
+        const int tn_mul = PAIR ? 2 : 1, tn_add = PAIR ? int(cta_rank) : 0;   // this CTA's image group of the pair's tile
         if (bstats && te == 0) {
-            twy.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
+            twy.init(wid + eg * wstep, EG * wstep, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
             for (int b = 0; b < ybufs && twy.valid(); ++b, twy.next()) issue_y(b);
         }
         int yk = 0;   // tiles this group has processed
         ptx::TileWalker tw;
-        for (tw.init(blockIdx.x + eg * gridDim.x, EG * gridDim.x, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid();
+        const uint32_t tempty_lead0 = PAIR ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
+        for (tw.init(wid + eg * wstep, EG * wstep, num_tiles, p.n_tiles, p.tiles_x, p.tiles_y); tw.valid();
              tw.next()) {
             const int n_tile = tw.n_tile;
-            const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = tw.tn * p.TN;
+            const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, n0 = (tw.tn * tn_mul + tn_add) * p.TN;
 
             // A box row outside the image still sees in-image neighbours through the
             // shifted taps, so its accumulator is not zero: zero it (the TMA store
@@ -561,7 +613,10 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
             // accumulator drained: hand the TMEM stage back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[a]);
+            if (lane == 0) {
+                if (PAIR && cta_rank != 0) ptx::mbar_arrive_cluster(tempty_lead0 + uint32_t(a) * 8u);
+                else ptx::mbar_arrive(&tempty_bar[a]);
+            }
             if (dbg_lead) SDN_DBG(2, dbg_tile, 3);
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(1 + eg, 128);
@@ -710,10 +765,12 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL>::THREADS), 1) co
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory and signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

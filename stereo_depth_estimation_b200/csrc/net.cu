@@ -160,6 +160,7 @@ struct GemmOp {
     ConvGemmParams p;
     int swa = 128, block_n = 32, grid = 1, smem = 0;
     bool swd64 = false;  // 128-wide tile stored as four 32-channel blocks (ConvTranspose2d with Cout = 32)
+    int ncta = 1;  // 2: CTA pairs (tcgen05 cta_group::2, cluster of two CTAs, each stages half of the weight rows)
     int halo = 0;  // 3x3 convs: 1 = row-halo A boxes (one per horizontal tap), 2 = one box for all nine taps; the packed weights use the matching K order
 };
 struct WgradOp {
@@ -306,17 +307,27 @@ static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
+static thread_local int t_cluster = 1;   // set by launch_cg around a CTA-pair launch (cluster dimension x)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     static const int pdl_env = env_int("SDN_PDL", -1);
     const int pdl = pdl_env >= 0 ? pdl_env : t_pdl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (t_cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)t_cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
@@ -327,7 +338,23 @@ static int launch_cg_t(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     CUDA_OK(cudaGetLastError());
     return 0;
 }
+template <int SWA, int BN, int HALO>
+static int launch_cg_pair(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    t_cluster = 2;
+    const cudaError_t e = launch_k(conv_gemm_kernel<SWA, BN, HALO, 0, 2>, op.grid, CgCfg<SWA, BN, 0, 2>::THREADS, op.smem, st, op.p);
+    t_cluster = 1;
+    ++c->launches;
+    CUDA_OK(e);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    if (op.ncta == 2) {
+        if (op.swa == 128 && op.block_n == 256 && op.halo == 0) return launch_cg_pair<128, 256, 0>(c, op, st);
+        if (op.swa == 128 && op.block_n == 128 && op.halo == 0) return launch_cg_pair<128, 128, 0>(c, op, st);
+        if (op.swa == 128 && op.block_n == 128 && op.halo == 1) return launch_cg_pair<128, 128, 1>(c, op, st);
+        return fail("no CTA-pair conv_gemm instantiation for swizzle %d, BLOCK_N %d, halo %d", op.swa, op.block_n, op.halo);
+    }
     if (op.swd64) {
         if (op.swa != 128 || op.block_n != 128 || op.halo != 0) return fail("swd64 needs the plain <128,128> kernel");
         launch_k(conv_gemm_kernel<128, 128, 0, 64>, op.grid, CgCfg<128, 128, 64>::THREADS, op.smem, st, op.p);
@@ -409,6 +436,7 @@ static int launch_wg(sdn_ctx* c, const WgradOp& op, cudaStream_t st) {
     CUDA_OK(cudaGetLastError());
     return 0;
 }
+static int g_max_pairs = 0;   // co-resident CTA pairs of the pair kernels (cudaOccupancyMaxActiveClusters)
 static int set_smem_attrs() {
     const int big = 227 * 1024;
 #define SDN_SMEM_ATTR(...) CUDA_OK(cudaFuncSetAttribute((conv_gemm_kernel<__VA_ARGS__>), cudaFuncAttributeMaxDynamicSharedMemorySize, big))
@@ -419,7 +447,19 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 32, 2); SDN_SMEM_ATTR(128, 64, 2); SDN_SMEM_ATTR(64, 32, 2); SDN_SMEM_ATTR(64, 64, 2);
     SDN_SMEM_ATTR(128, 64, 3);
     SDN_SMEM_ATTR(128, 128, 0, 64);
+    SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
 #undef SDN_SMEM_ATTR
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(CgCfg<128, 256, 0, 2>::THREADS); cfg.dynamicSmemBytes = 200 * 1024;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<128, 256, 0, 0, 2>, &cfg) == cudaSuccess && n > 0) g_max_pairs = n;
+        else (void)cudaGetLastError();
+    }
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -694,6 +734,20 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     p.tiles_x = (W + t.TW - 1) / t.TW;
     p.tiles_y = (H + t.TH - 1) / t.TH;
     p.tiles_n = (B + t.TN - 1) / t.TN;
+    // CTA pairs (conv_gemm NCTA = 2): wide tiles, the two CTAs take consecutive image groups of one tile position
+    static const int cta2_on = env_int("SDN_CTA2", 1);
+    op.ncta = 1;
+    // (short K loops lose to the pair's extra handshakes - measured: 64 -> 128 3x3 at N = 128 and the level-1/2
+    // ConvTranspose2d GEMMs got 10-25 % slower, everything with K * N >= 512 * 256 got 20-35 % faster)
+    int k_total = 0;
+    for (const SegSpec& sg : segs) k_total += aviews[sg.view].C * (op.halo ? 3 : 1);
+    static const int cta2_min_kn = env_int("SDN_CTA2_MIN_KN", 512 * 256);
+    if (cta2_on && bn >= 128 && op.halo <= 1 && !op.swd64 && op.swa == 128 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16) &&
+        (long long)k_total * bn >= cta2_min_kn) {
+        op.ncta = 2;
+        p.tiles_n = (p.tiles_n + 1) / 2;   // the kernel walks pairs of image groups
+    }
+    const int bn_loc = bn / op.ncta;       // weight rows this CTA stages
     p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
@@ -714,8 +768,8 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         kblocks += g.cblocks;
     }
     p.kblocks_total = kblocks;
-    if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * (op.halo == 2 ? 9 : 3), bn, op.swa));
-    else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn, op.swa));
+    if (op.halo) SDN_OK(encode3(&p.b_map, bmat, KB, n_total, kblocks * (op.halo == 2 ? 9 : 3), bn_loc, op.swa));
+    else SDN_OK(encode2(&p.b_map, bmat, kblocks * KB, n_total, KB, bn_loc, op.swa));
     const int swd = op.swd64 ? 64 : ((bn >= 64 && op.swa == 128) ? 128 : 64);
     const int dch = swd / 2;
     if (n_per_dmap % dch != 0) return fail("build_gemm: destination width %d not a multiple of the %d-channel store block", n_per_dmap, dch);
@@ -766,12 +820,12 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     } else if (op.halo) {
         // weights resident in shared memory when the whole packed matrix of this N tile fits;
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
-        const int b_total = kblocks * 3 * bn * op.swa;
+        const int b_total = kblocks * 3 * bn_loc * op.swa;
         static const int ups_on = env_int("SDN_UPS", 3);
         const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
         if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
-        const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn * op.swa);
+        const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn_loc * op.swa);
         const int budget = 220 * 1024 - fixed - (res ? b_total : 0);
         p.ups = (ups_on == 3 && kblocks % 3 == 0 && budget / (3 * unit_bytes) >= 4) ? 3 : 1;
         stages = std::max(2, std::min(8, budget / (p.ups * unit_bytes)));
@@ -781,13 +835,15 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
             while (stages > 2 && CgCfg<128, 128, 64>::smem_bytes(stages) > 220 * 1024) --stages;
             op.smem = CgCfg<128, 128, 64>::smem_bytes(stages);
         } else {
-            while (stages > 2 && cg_smem(op.swa, bn, stages) + ybytes > 220 * 1024) --stages;
-            op.smem = cg_smem(op.swa, bn, stages) + ybytes;
+            const int stage_bytes = 128 * op.swa + bn_loc * op.swa;
+            while (stages > 2 && cg_smem(op.swa, bn, 0) + stages * stage_bytes + ybytes > 220 * 1024) --stages;
+            op.smem = cg_smem(op.swa, bn, 0) + stages * stage_bytes + ybytes;
         }
     }
     p.stages = stages;
     const int num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
-    op.grid = std::max(1, std::min(num_tiles, c->num_sms));
+    op.grid = op.ncta == 2 ? 2 * std::max(1, std::min(num_tiles, g_max_pairs > 0 ? g_max_pairs : c->num_sms / 2))
+                           : std::max(1, std::min(num_tiles, c->num_sms));
     return 0;
 }
 
