@@ -418,6 +418,22 @@ __global__ void bn_prepare_eval_kernel(int C, const float* __restrict__ gamma, c
     if (C == 32) { scale[c + 32] = sc; shift[c + 32] = shift[c]; }   // super-pixel view (conv_gemm HALO = 3)
 }
 
+// Walks the 2x2 quads q0, q0 + qstep, ... of a [B, H/2, W/2] quad grid WITHOUT per-item divisions (the 64-bit
+// div / mod chain of the index decode was ~450 of the ~750 instructions per item of the pooled kernels).
+struct QuadWalker {
+    int x2, y2, n, dx, dy, dn, W2, H2;
+    __device__ __forceinline__ void init(long long q0, long long qstep, int W2_, int H2_) {
+        W2 = W2_; H2 = H2_;
+        x2 = int(q0 % W2); long long m = q0 / W2; y2 = int(m % H2); n = int(m / H2);
+        dx = int(qstep % W2); m = qstep / W2; dy = int(m % H2); dn = int(m / H2);
+    }
+    __device__ __forceinline__ void next() {
+        x2 += dx; int c = x2 >= W2 ? 1 : 0; x2 -= c * W2;
+        y2 += dy + c; c = y2 >= H2 ? 1 : 0; y2 -= c * H2;
+        n += dn + c;
+    }
+};
+
 // a = relu(y*scale + shift), optionally also p = maxpool2x2(a).
 // POOL: one thread = a 2x2 pixel quad x 8 channels.  Otherwise one pixel x 8 channels.
 template <bool POOL>
@@ -440,12 +456,11 @@ __global__ void bn_relu_pool_kernel(const bf16* __restrict__ y, const float* __r
     if (POOL) {
         const int H2 = H >> 1, W2 = W >> 1;
         const long long total = (long long)B * H2 * W2 * CG;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long qd = i / CG;
-            const int x2 = int(qd % W2);
-            const int y2 = int((qd / W2) % H2);
-            const int n = int(qd / ((long long)W2 * H2));
+        const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+        QuadWalker qw;
+        qw.init(tid0 / CG, stride / CG, W2, H2);     // (the stride is a multiple of CG: this thread keeps its channel group)
+        for (long long i = tid0; i < total; i += stride, qw.next()) {
+            const int x2 = qw.x2, y2 = qw.y2, n = qw.n;
             float mx[8];
             unsigned am = 0;   // 2 bits per channel: quad position of the FIRST maximum (nn.MaxPool2d routing)
 #pragma unroll
@@ -521,21 +536,67 @@ __global__ void maxpool2x2_kernel(const bf16* __restrict__ a, bf16* __restrict__
 // One work item = 8 channels of one pixel (or of one 2x2 quad when POOL).  APPLY = false:
 // accumulate the two per-channel sums; APPLY = true: write dy.  The quad variant keeps only
 // the raw bf16 y vectors and the running arg-max in registers (two passes over the quad).
+// Packed fp32 pairs (FFMA2 / FADD2 on sm_100): these kernels are ISSUE-bound, not bandwidth-bound (the pooled
+// variants ran ~14 instructions per element at 70-79 % of HBM), so channel pairs (2k, 2k+1) travel as float2.
+__device__ __forceinline__ void unpack8_2(const uint4& q, float2 (&f)[4]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint4 pack8_2(const float2 (&f)[4]) {
+    uint4 q;
+    q.x = pack2(f[0].x, f[0].y); q.y = pack2(f[1].x, f[1].y); q.z = pack2(f[2].x, f[2].y); q.w = pack2(f[3].x, f[3].y);
+    return q;
+}
+// per-thread coefficients of one 8-channel group: z = y*sc + sh (ReLU gate), ym = y + nmu (= y - mean);
+// apply:  dy = sc*dz + kb*ym + kc  with  kb = -sc*c2*rstd, kc = -sc*c1   (== sc * (dz - c1 - xhat*c2))
+struct BnBwdCoef {
+    float2 sc[4], sh[4], nmu[4], kb[4], kc[4];
+};
+template <bool APPLY>
+__device__ __forceinline__ void bn_bwd_coef_load(BnBwdCoef& k, int cg, const float* __restrict__ scale,
+                                                 const float* __restrict__ shift, const float* __restrict__ mean,
+                                                 const float* __restrict__ rstd, const float* __restrict__ c1,
+                                                 const float* __restrict__ c2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = cg * 8 + 2 * j;
+        k.sc[j] = make_float2(scale[c], scale[c + 1]);
+        k.sh[j] = make_float2(shift[c], shift[c + 1]);
+        k.nmu[j] = make_float2(-mean[c], -mean[c + 1]);
+        if (APPLY) {
+            k.kb[j] = make_float2(-k.sc[j].x * c2[c] * rstd[c], -k.sc[j].y * c2[c + 1] * rstd[c + 1]);
+            k.kc[j] = make_float2(-k.sc[j].x * c1[c], -k.sc[j].y * c1[c + 1]);
+        }
+    }
+}
+// one pixel x 8 channels: yq / gq raw bf16 vectors, `route` = pooled gradient to add where the arg-max mask says so
+template <bool APPLY>
+__device__ __forceinline__ uint4 bn_bwd_px(const BnBwdCoef& k, const uint4& yq, const uint4& gq, float2 (&s1)[4],
+                                           float2 (&s2)[4]) {
+    float2 y2[4], g2[4], o[4];
+    unpack8_2(yq, y2);
+    unpack8_2(gq, g2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 z = __ffma2_rn(y2[j], k.sc[j], k.sh[j]);
+        const float2 dz = make_float2(z.x > 0.f ? g2[j].x : 0.f, z.y > 0.f ? g2[j].y : 0.f);
+        const float2 ym = __fadd2_rn(y2[j], k.nmu[j]);
+        if (APPLY) o[j] = __ffma2_rn(k.kb[j], ym, __ffma2_rn(k.sc[j], dz, k.kc[j]));
+        else { s1[j] = __fadd2_rn(s1[j], dz); s2[j] = __ffma2_rn(dz, ym, s2[j]); }
+    }
+    return APPLY ? pack8_2(o) : uint4{0u, 0u, 0u, 0u};
+}
+// One work item = 8 channels of one pixel (or of one 2x2 quad when POOL).  APPLY = false: accumulate
+// s1 = sum dz and s2 = sum dz * (y - mean) (the finalize kernel multiplies s2 by rstd); APPLY = true: write dy.
 template <bool POOL, bool APPLY>
 __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf16* __restrict__ g,
                                             const bf16* __restrict__ gp, const unsigned short* __restrict__ amax,
-                                            const float (&sc)[8], const float (&sh)[8],
-                                            const float (&mu)[8], const float (&rs)[8], const float (&k1)[8],
-                                            const float (&k2)[8], long long i, int H, int W, int C, float (&s1)[8],
-                                            float (&s2)[8], bf16* __restrict__ dy) {
-    const int CG = C >> 3;
-    const int cg = int(i % CG);
+                                            const BnBwdCoef& k, long long i, int cg, const QuadWalker& qw, int H, int W,
+                                            int C, float2 (&s1)[4], float2 (&s2)[4], bf16* __restrict__ dy) {
     if (POOL) {
         const int H2 = H >> 1, W2 = W >> 1;
-        const long long qd = i / CG;
-        const int x2 = int(qd % W2);
-        const int y2 = int((qd / W2) % H2);
-        const int n = int(qd / ((long long)W2 * H2));
+        const int x2 = qw.x2, y2 = qw.y2, n = qw.n;
         const long long p00 = ((long long)n * H + 2 * y2) * W + 2 * x2;
         const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
         // the forward stored which quad position won each channel's max (first maximum, bf16 values)
@@ -546,37 +607,36 @@ __device__ __forceinline__ void bn_bwd_item(const bf16* __restrict__ y, const bf
             yr[d] = ldg16(y + pix[d] * C + cg * 8);
             gr[d] = ldg16(g + pix[d] * C + cg * 8);
         }
-        float gpf[8];
-        unpack8(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gpf);
+        float2 gp2[4];
+        unpack8_2(ldg16(gp + (((long long)n * H2 + y2) * W2 + x2) * C + cg * 8), gp2);
+        unsigned amj[8];     // each channel's 2-bit field, left in place: compared with d << (2 * j)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) amj[j] = am & (3u << (2 * j));
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            float yf[8], gf[8], o[8];
-            unpack8(yr[d], yf);
-            unpack8(gr[d], gf);
+            // route the pooled gradient: dA = g + (arg-max == d ? gp : 0), added in fp32 like autograd's accumulation
+            float2 g2[4];
+            unpack8_2(gr[d], g2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float z = fmaf(yf[j], sc[j], sh[j]);
-                const float da = gf[j] + (((am >> (2 * j)) & 3u) == unsigned(d) ? gpf[j] : 0.f);
-                const float dz = z > 0.f ? da : 0.f;
-                const float xh = (yf[j] - mu[j]) * rs[j];
-                if (APPLY) o[j] = sc[j] * (dz - k1[j] - xh * k2[j]);
-                else { s1[j] += dz; s2[j] = fmaf(dz, xh, s2[j]); }
+            for (int j = 0; j < 4; ++j) {
+                if (amj[2 * j] == (unsigned(d) << (4 * j))) g2[j].x += gp2[j].x;
+                if (amj[2 * j + 1] == (unsigned(d) << (4 * j + 2))) g2[j].y += gp2[j].y;
             }
-            if (APPLY) *reinterpret_cast<uint4*>(dy + pix[d] * C + cg * 8) = pack8(o);
+            float2 y2v[4], o[4];
+            unpack8_2(yr[d], y2v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 z = __ffma2_rn(y2v[j], k.sc[j], k.sh[j]);
+                const float2 dz = make_float2(z.x > 0.f ? g2[j].x : 0.f, z.y > 0.f ? g2[j].y : 0.f);
+                const float2 ym = __fadd2_rn(y2v[j], k.nmu[j]);
+                if (APPLY) o[j] = __ffma2_rn(k.kb[j], ym, __ffma2_rn(k.sc[j], dz, k.kc[j]));
+                else { s1[j] = __fadd2_rn(s1[j], dz); s2[j] = __ffma2_rn(dz, ym, s2[j]); }
+            }
+            if (APPLY) *reinterpret_cast<uint4*>(dy + pix[d] * C + cg * 8) = pack8_2(o);
         }
     } else {
-        float yf[8], gf[8], o[8];
-        unpack8(ldg16(y + i * 8), yf);
-        unpack8(ldg16(g + i * 8), gf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(yf[j], sc[j], sh[j]);
-            const float dz = z > 0.f ? gf[j] : 0.f;
-            const float xh = (yf[j] - mu[j]) * rs[j];
-            if (APPLY) o[j] = sc[j] * (dz - k1[j] - xh * k2[j]);
-            else { s1[j] += dz; s2[j] = fmaf(dz, xh, s2[j]); }
-        }
-        if (APPLY) *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+        const uint4 o = bn_bwd_px<APPLY>(k, ldg16(y + i * 8), ldg16(g + i * 8), s1, s2);
+        if (APPLY) *reinterpret_cast<uint4*>(dy + i * 8) = o;
     }
 }
 
@@ -594,17 +654,24 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_reduce_kernel(const 
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = int(tid0 % CG);  // fixed per thread: the stride is a multiple of CG
-    float sc[8], sh[8], mu[8], rs[8], s1[8], s2[8];
+    BnBwdCoef k;
+    bn_bwd_coef_load<false>(k, cg, scale, shift, mean, rstd, nullptr, nullptr);
+    float2 s1[4], s2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
-        s1[j] = 0.f; s2[j] = 0.f;
+    for (int j = 0; j < 4; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    QuadWalker qw;
+    if (POOL) qw.init(tid0 / CG, stride / CG, W >> 1, H >> 1);
+    for (long long i = tid0; i < total; i += stride) {
+        bn_bwd_item<POOL, false>(y, g, gp, amax, k, i, cg, qw, H, W, C, s1, s2, nullptr);
+        if (POOL) qw.next();
     }
-    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
-        bn_bwd_item<POOL, false>(y, g, gp, amax, sc, sh, mu, rs, sc, sc, i, H, W, C, s1, s2, nullptr);
     __shared__ float red[256][17];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
+    for (int j = 0; j < 4; ++j) {
+        red[threadIdx.x][2 * j] = s1[j].x; red[threadIdx.x][2 * j + 1] = s1[j].y;
+        red[threadIdx.x][8 + 2 * j] = s2[j].x; red[threadIdx.x][8 + 2 * j + 1] = s2[j].y;
+    }
     __syncthreads();
     // thread t < 2*C reduces one (sum kind, channel) over the threads that share its channel group
     for (int o = threadIdx.x; o < 2 * C; o += blockDim.x) {
@@ -662,15 +729,28 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3) bn_bwd_apply_kernel(const b
     const int CG = C >> 3;
     const long long total = POOL ? (long long)B * (H >> 1) * (W >> 1) * CG : (long long)B * H * W * CG;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     const int cg = int(tid0 % CG);
-    float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8], s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
-        k1[j] = c1[cg * 8 + j]; k2[j] = c2[cg * 8 + j];
+    BnBwdCoef k;
+    bn_bwd_coef_load<true>(k, cg, scale, shift, mean, rstd, c1, c2);
+    float2 s1[4], s2[4];   // (unused by the apply pass)
+    if (POOL) {
+        QuadWalker qw;
+        qw.init(tid0 / CG, stride / CG, W >> 1, H >> 1);
+        for (long long i = tid0; i < total; i += stride, qw.next())
+            bn_bwd_item<true, true>(y, g, gp, amax, k, i, cg, qw, H, W, C, s1, s2, dy);
+    } else {
+        // two items per iteration, all four 16-byte loads issued before the first use: at three blocks per SM one
+        // item per thread kept only 24 KB per SM in flight, below what the HBM latency needs
+        long long i = tid0;
+        for (; i + stride < total; i += 2 * stride) {
+            const uint4 y0 = ldg16(y + i * 8), g0 = ldg16(g + i * 8);
+            const uint4 y1 = ldg16(y + (i + stride) * 8), g1 = ldg16(g + (i + stride) * 8);
+            *reinterpret_cast<uint4*>(dy + i * 8) = bn_bwd_px<true>(k, y0, g0, s1, s2);
+            *reinterpret_cast<uint4*>(dy + (i + stride) * 8) = bn_bwd_px<true>(k, y1, g1, s1, s2);
+        }
+        if (i < total) *reinterpret_cast<uint4*>(dy + i * 8) = bn_bwd_px<true>(k, ldg16(y + i * 8), ldg16(g + i * 8), s1, s2);
     }
-    for (long long i = tid0; i < total; i += (long long)gridDim.x * blockDim.x)
-        bn_bwd_item<POOL, true>(y, g, gp, amax, sc, sh, mu, rs, k1, k2, i, H, W, C, s1, s2, dy);
 }
 
 // ConvTranspose2d bias gradient from the per-CTA column sums that the producing dgrad's epilogue

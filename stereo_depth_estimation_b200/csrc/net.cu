@@ -1441,7 +1441,7 @@ static int bn_backward(sdn_ctx* c, ConvL& L, int B, cudaStream_t st) {
                                                               c->bwd_partials, B, H, W, C);
         ++c->launches;
         launch_k(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, c->bwd_partials, grid, C, count, L.c1, L.c2,
-                                                                c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)nullptr, 1);
+                                                                c->grads[L.p_gamma], c->grads[L.p_beta], c->accumulate, (const float*)L.rstd, 1);
         ++c->launches;
     }
     if (pool)
