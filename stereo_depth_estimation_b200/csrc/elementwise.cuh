@@ -914,7 +914,16 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const bf16* __restri
         // lane receives the two seeds through shuffles
         float dzd = 0.f, dzl = 0.f;
         if (half == 0 && active) {
-            const float dsp = zd > 20.f ? zd : log1pf(expf(zd));
+            // softplus / sigmoid / exp on the special-function unit (the scalar chain of this lane is the kernel's
+            // critical path): log1p(e) as its series below e = exp(-5) (error e^4/4 < 1e-7 relative), __logf(1 + e)
+            // above it (<= 1e-5 relative); -DSDN_AUG_PRECISE restores libm
+#ifdef SDN_AUG_PRECISE
+            const float ez = expf(fminf(zd, 20.f));
+            const float dsp = zd > 20.f ? zd : log1pf(ez);
+#else
+            const float ez = __expf(fminf(zd, 20.f));
+            const float dsp = zd > 20.f ? zd : (zd < -5.f ? ez * (1.f - ez * (0.5f - ez * (1.f / 3.f))) : __logf(1.f + ez));
+#endif
             const float lv = fminf(fmaxf(zl, -6.f), 3.f);
             if (MODE != 1) {
                 if (disp != nullptr) disp[p] = dsp;
@@ -932,18 +941,30 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const bf16* __restri
                     if (m) {
                         const float diff = dsp - tg;
                         const float ad = fabsf(diff);
+#ifdef SDN_AUG_PRECISE
                         const float e = expf(-lv);
+#else
+                        const float e = __expf(-lv);
+#endif
                         acc[34] += ad * e + lv;
                         acc[35] += ad;
                         acc[36] = fmaf(diff, diff, acc[36]);
+#ifdef SDN_AUG_PRECISE
                         acc[37] += expf(0.5f * lv);
+#else
+                        acc[37] += rsqrtf(e);          // exp(lv / 2) = exp(-lv)^(-1/2)
+#endif
                         acc[38] += 1.f;
                         const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
                         gd = sg * e * inv_n;
                         gl = (1.f - ad * e) * inv_n;
                     }
                 }
+#ifdef SDN_AUG_PRECISE
                 const float sig = zd > 20.f ? 1.f : 1.f / (1.f + expf(-zd));
+#else
+                const float sig = zd > 20.f ? 1.f : __fdividef(ez, 1.f + ez);     // e^z / (1 + e^z)
+#endif
                 dzd = gd * sig;
                 dzl = (zl >= -6.f && zl <= 3.f) ? gl : 0.f;
             }
