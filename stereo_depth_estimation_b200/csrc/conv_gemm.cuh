@@ -84,7 +84,7 @@ struct alignas(64) ConvGemmParams {
 #define SDN_ABLATE(flag) false
 #endif
 
-template <int SWA, int BLOCK_N, int SWD_SEL = 0, int NCTA = 1>
+template <int SWA, int BLOCK_N, int SWD_SEL = 0, int NCTA = 1, int EGSEL = 0>
 struct CgCfg {
     static constexpr int KB = SWA / 2;  // bf16 channels per k-block
     static constexpr int A_BYTES = 128 * SWA;
@@ -104,7 +104,9 @@ struct CgCfg {
     static constexpr int RG = 128 / WPR;    // row groups in the stats pass
     // small-N tiles are epilogue-bound (the per-tile bookkeeping of a 128-thread epilogue is longer than
     // their main loop): two epilogue warpgroups, one per TMEM accumulator stage, take alternate tiles
-    static constexpr int EG = BLOCK_N <= 64 ? 2 : 1;
+    // (EGSEL = 2: N = 128 tiles with a SHORT K loop - the ConvTranspose2d GEMMs, 1-4 k-blocks per tile - have the same
+    // problem: one epilogue group with one staging buffer waited for the previous tile's TMA store to drain)
+    static constexpr int EG = EGSEL ? EGSEL : (BLOCK_N <= 64 ? 2 : 1);
     // -DSDN_TWO_MMA_WARPS: two MMA-issuing warps (one per TMEM stage / epilogue group), an experiment kept for
     // reference: the pipe is not idle between tiles, so interleaving two tiles only delays both epilogues
 #ifdef SDN_TWO_MMA_WARPS
@@ -123,7 +125,7 @@ struct CgCfg {
     static constexpr int SCRATCH_BYTES = EG * RG * BLOCK_N * 2 * 4;
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
-    static constexpr int DBUF = BLOCK_N <= 64 ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
+    static constexpr int DBUF = (BLOCK_N <= 64 || EGSEL == 2) ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
     static constexpr int NT = BLOCK_N >= 128 ? 512 / BLOCK_N : 1;    // N tiles a stats layer can have (Cout <= 512)
     static constexpr int smem_bytes(int stages) {
         return 1024 + stages * STAGE_BYTES + DBUF * D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;
@@ -178,9 +180,9 @@ __device__ __forceinline__ void cg_commit(uint64_t* bar) {
     else ptx::tc_commit(bar);
 }
 
-template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0, int NCTA = 1>
-__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA>;
+template <int SWA, int BLOCK_N, int HALO, int SWD_SEL = 0, int NCTA = 1, int EGSEL = 0>
+__global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>::THREADS), 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>;
     constexpr int KB = Cfg::KB;
     constexpr bool PAIR = NCTA == 2;
     static_assert(!PAIR || (HALO <= 1 && Cfg::EG == 1 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo kernels with N >= 128");

@@ -160,6 +160,7 @@ struct GemmOp {
     ConvGemmParams p;
     int swa = 128, block_n = 32, grid = 1, smem = 0;
     bool swd64 = false;  // 128-wide tile stored as four 32-channel blocks (ConvTranspose2d with Cout = 32)
+    int eg = 1;    // epilogue warpgroups of the kernel (partial-statistics rows per CTA)
     int ncta = 1;  // 2: CTA pairs (tcgen05 cta_group::2, cluster of two CTAs, each stages half of the weight rows)
     int halo = 0;  // 3x3 convs: 1 = row-halo A boxes (one per horizontal tap), 2 = one box for all nine taps; the packed weights use the matching K order
 };
@@ -349,6 +350,13 @@ static int launch_cg_pair(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     return 0;
 }
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
+    if (op.eg == 2 && op.block_n == 128) {
+        if (!(op.swa == 128 && op.halo == 0 && !op.swd64 && op.ncta == 1)) return fail("two epilogue groups at N = 128: plain kernel only");
+        launch_k(conv_gemm_kernel<128, 128, 0, 0, 1, 2>, op.grid, CgCfg<128, 128, 0, 1, 2>::THREADS, op.smem, st, op.p);
+        ++c->launches;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (op.ncta == 2) {
         if (op.swa == 128 && op.block_n == 256 && op.halo == 0) return launch_cg_pair<128, 256, 0>(c, op, st);
         if (op.swa == 128 && op.block_n == 128 && op.halo == 0) return launch_cg_pair<128, 128, 0>(c, op, st);
@@ -448,6 +456,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 64, 3);
     SDN_SMEM_ATTR(128, 128, 0, 64);
     SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
+    SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2);
 #undef SDN_SMEM_ATTR
     {
         cudaLaunchConfig_t cfg = {};
@@ -568,7 +577,7 @@ static int build_gemm_superpixel(sdn_ctx* c, GemmOp& op, int B, const std::vecto
                                  const BStatSpec* bs) {
     memset(&op.p, 0, sizeof op.p);
     ConvGemmParams& p = op.p;
-    op.swa = 128; op.block_n = 64; op.halo = 3; op.swd64 = false;
+    op.swa = 128; op.block_n = 64; op.halo = 3; op.swd64 = false; op.eg = 2; op.ncta = 1;
     const SrcView d = super_view(dview);
     const int W = d.W, H = d.H, units = (int)aviews.size();
     p.TW = 8; p.TH = 16; p.TN = 1;
@@ -650,6 +659,13 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         }
     }
     if (op.swa == 64 && bn > 64) bn = 64;
+    // short K loops (ConvTranspose2d GEMMs: 1-4 k-blocks per tile) are epilogue-bound: N = 128 tiles with two
+    // epilogue groups and two staging buffers instead of one N = 256 / N = 128 tile drained by one group
+    int kb_est = 0;
+    for (const SegSpec& sg : segs_in) kb_est += aviews[sg.view].C / 64;
+    static const int eg2_on = env_int("SDN_EG2", 1);
+    const bool short_k = eg2_on && !conv3x3 && op.swa == 128 && kb_est <= 4 && !op.swd64 && n_per_dmap % 64 == 0;
+    if (short_k && bn == 256) bn = 128;
     const int W = dviews[0].W, H = dviews[0].H;
     if (bn == 256 && n_per_dmap % 128 == 0) {
         // Wave quantisation on the small levels: a persistent grid of num_sms CTAs runs ceil(jobs / num_sms)
@@ -748,6 +764,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         p.tiles_n = (p.tiles_n + 1) / 2;   // the kernel walks pairs of image groups
     }
     const int bn_loc = bn / op.ncta;       // weight rows this CTA stages
+    op.eg = (bn <= 64 || (short_k && bn == 128 && op.halo == 0 && op.ncta == 1)) ? 2 : 1;
     p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
@@ -788,7 +805,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         p.bs_scale = bs->scale; p.bs_shift = bs->shift; p.bs_mean = bs->mean;
         // small tiles are epilogue-bound: fetch y two tiles ahead; wide tiles hide one fetch behind their main loop
         p.ybuf = bn <= 64 ? 2 : 1;
-        ybytes = (bn <= 64 ? 2 : 1) * p.ybuf * 128 * bn * 2;
+        ybytes = op.eg * p.ybuf * 128 * bn * 2;
     } else {
         p.y_map = p.d_maps[0];
         p.ybuf = 1;
@@ -836,8 +853,9 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
             op.smem = CgCfg<128, 128, 64>::smem_bytes(stages);
         } else {
             const int stage_bytes = 128 * op.swa + bn_loc * op.swa;
-            while (stages > 2 && cg_smem(op.swa, bn, 0) + stages * stage_bytes + ybytes > 220 * 1024) --stages;
-            op.smem = cg_smem(op.swa, bn, 0) + stages * stage_bytes + ybytes;
+            const int fixed = (op.eg == 2 && bn == 128) ? CgCfg<128, 128, 0, 1, 2>::smem_bytes(0) : cg_smem(op.swa, bn, 0);
+            while (stages > 2 && fixed + stages * stage_bytes + ybytes > 220 * 1024) --stages;
+            op.smem = fixed + stages * stage_bytes + ybytes;
         }
     }
     p.stages = stages;
@@ -1155,7 +1173,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
                               target ? &bspec : nullptr));
             if (target != nullptr) {
                 target->bwd_stats_fused = (L.dgrad.p.flags & CG_BSTATS) != 0;
-                target->bwd_stats_parts = L.dgrad.grid * (L.dgrad.block_n <= 64 ? 2 : 1);
+                target->bwd_stats_parts = L.dgrad.grid * L.dgrad.eg;
                 target->bwd_stats_fold = L.dgrad.halo == 3 ? 2 : 1;
             }
             if (L.nsrc == 2) {
@@ -1198,7 +1216,7 @@ static int prepare_batch(sdn_ctx* c, int B) {
         SDN_OK(build_gemm(c, U.dgrad, B, quads_gu, qsegs, U.wd, U.cin, {full_view(T.ga)}, U.cin, nullptr, 0, nullptr, false, 3,
                           &bspec));
         T.bwd_stats_fused = (U.dgrad.p.flags & CG_BSTATS) != 0;
-        T.bwd_stats_parts = U.dgrad.grid * (U.dgrad.block_n <= 64 ? 2 : 1);
+        T.bwd_stats_parts = U.dgrad.grid * U.dgrad.eg;
         T.bwd_stats_fold = 1;
         SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
     }
@@ -1395,7 +1413,7 @@ static int forward_impl(sdn_ctx* c, const float* x, float* disp, float* logvar, 
         if (training) {
             const double count = (double)B * L.y.H * L.y.W;
             launch_k(bn_finalize_train_kernel, (L.cout * 32 + 255) / 256, 256, 0, st, 
-                c->stats_partials, op.grid * (op.block_n <= 64 ? 2 : 1), L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
+                c->stats_partials, op.grid * op.eg, L.cout, count, c->params[L.p_gamma], c->params[L.p_beta], c->bn_rm[L.bn],
                 c->bn_rv[L.bn], (long long*)c->bn_nbt[L.bn], 1e-5f, 0.1f, L.scale, L.shift, L.mean, L.rstd, op.halo == 3 ? 2 : 1);
             ++c->launches;
         }
@@ -1499,7 +1517,7 @@ static int conv_backward(sdn_ctx* c, int i, int B, cudaStream_t st) {
     if (L.has_dgrad && L.nsrc == 2 && c->up[(i - 10) / 2].bias_fused) {
         UpL& U = c->up[(i - 10) / 2];
         launch_k(colsum_partials_kernel, (U.cout * 32 + 255) / 256, 256, 0, st, c->stats_partials,
-                 L.dgrad.grid * (L.dgrad.block_n <= 64 ? 2 : 1), L.dgrad.p.n_total, U.cout, U.bg);
+                 L.dgrad.grid * L.dgrad.eg, L.dgrad.p.n_total, U.cout, U.bg);
         ++c->launches;
     }
     CUDA_OK(cudaGetLastError());
