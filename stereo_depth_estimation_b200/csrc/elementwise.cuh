@@ -1121,12 +1121,16 @@ __global__ void __launch_bounds__(256) adamw_all_kernel(const __grid_constant__ 
 __global__ void unpack_grad_kernel(const float* __restrict__ ws, float* __restrict__ grad, int mode, int Co, int Ci,
                                    int accumulate) {
     SDN_PDL_ENTRY();
-    const int total = (mode == 3) ? 4 * Co * Ci : 9 * Co * Ci;
+    const int total = (mode == 3 || mode == 5) ? 4 * Co * Ci : 9 * Co * Ci;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v;
         if (mode == 3) {
             const int ci = i / (Co * 4), rem = i % (Co * 4), co = rem / 4, q = rem % 4;
             v = ws[((size_t)q * Ci + ci) * Co + co];
+        } else if (mode == 5) {
+            // ConvTranspose2d, quadrant PAIRS as the dY variants: ws[i2][ci][j * Co + co], quadrant q = 2 * i2 + j
+            const int ci = i / (Co * 4), rem = i % (Co * 4), co = rem / 4, q = rem % 4;
+            v = ws[((size_t)(q >> 1) * Ci + ci) * (2 * Co) + (q & 1) * Co + co];
         } else if (mode == 4) {
             // first layer, row-halo form: ws[((dy*3 + 1)*32 + dx*Ci + c)][Co] -> grad[Co][Ci][3][3]
             const int co = i / (Ci * 9), rem = i % (Ci * 9), ci = rem / 9, tap = rem % 9;

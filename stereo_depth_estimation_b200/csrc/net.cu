@@ -194,6 +194,7 @@ struct ConvL {  // conv3x3 + BatchNorm + ReLU
     int bwd_stats_fold = 1;   // 2: the producer ran in the super-pixel view (partial rows hold 2 x C columns)
 };
 struct UpL {  // ConvTranspose2d(k=2, s=2)
+    bool wgrad_pairs = false;   // dY variants of the weight gradient are quadrant pairs (workspace layout of unpack mode 5)
     int cin = 0, cout = 0, lvl_in = 0;
     const Act* src = nullptr;
     int src_layer = 0;
@@ -1218,7 +1219,12 @@ static int prepare_batch(sdn_ctx* c, int B) {
         T.bwd_stats_fused = (U.dgrad.p.flags & CG_BSTATS) != 0;
         T.bwd_stats_parts = U.dgrad.grid * U.dgrad.eg;
         T.bwd_stats_fold = 1;
-        SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
+        // weight gradient: the same pairing halves the dY variants (dense 128-byte rows instead of half-filled
+        // ones, the source tile read twice instead of four times); workspace [2][cin][2 * cout] (unpack mode 5)
+        static const int wpair_on = env_int("SDN_CONVT_WGRAD_PAIRS", 1);
+        U.wgrad_pairs = pair_on && wpair_on;
+        if (U.wgrad_pairs) SDN_OK(build_wgrad(c, U.wgrad, B, pairs_gu, 2 * U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
+        else SDN_OK(build_wgrad(c, U.wgrad, B, quads_gu, U.cout, {full_view(*U.src)}, 1, U.wg, U.cin));
     }
     c->B = B;
     return 0;
@@ -1554,7 +1560,7 @@ static int up_backward(sdn_ctx* c, int k, int B, cudaStream_t st) {
                   pxin * (U.cin * ((U.dgrad.p.flags & CG_BSTATS) ? 2 : 1) + 4 * U.cout) * 2);
     if (c->grads[U.p_w] != nullptr) {
         const int n = 4 * U.cin * U.cout;
-        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, U.wg, c->grads[U.p_w], 3, U.cout, U.cin, c->accumulate);
+        launch_k(unpack_grad_kernel, occ_grid(c, unpack_grad_kernel, n, 256), 256, 0, ws, U.wg, c->grads[U.p_w], U.wgrad_pairs ? 5 : 3, U.cout, U.cin, c->accumulate);
         ++c->launches;
     }
     if (c->grads[U.p_b] != nullptr) {
