@@ -125,9 +125,7 @@ struct CgCfg {
     static constexpr int SCRATCH_BYTES = EG * RG * BLOCK_N * 2 * 4;
     static constexpr int ACC_BYTES = 2 * 512 * 4;
     static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
-    // (EGSEL = 1: ONE group but two staging buffers - 3x3 convs at N = 128 with K = 576: their main loop is shorter than
-    // the drain of the previous tile's 32 KB TMA store, which a single buffer has to wait for)
-    static constexpr int DBUF = (BLOCK_N <= 64 || EGSEL != 0) ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
+    static constexpr int DBUF = (BLOCK_N <= 64 || EGSEL == 2) ? 2 : 1;   // staging buffers (small tiles: defer the store-read wait)
     static constexpr int NT = BLOCK_N >= 128 ? 512 / BLOCK_N : 1;    // N tiles a stats layer can have (Cout <= 512)
     static constexpr int smem_bytes(int stages) {
         return 1024 + stages * STAGE_BYTES + DBUF * D_BYTES + SCRATCH_BYTES + ACC_BYTES + 256;

@@ -161,7 +161,6 @@ struct GemmOp {
     int swa = 128, block_n = 32, grid = 1, smem = 0;
     bool swd64 = false;  // 128-wide tile stored as four 32-channel blocks (ConvTranspose2d with Cout = 32)
     int eg = 1;    // epilogue warpgroups of the kernel (partial-statistics rows per CTA)
-    bool dbuf2 = false;   // row-halo N = 128 kernel with two staging buffers (short K loops)
     int ncta = 1;  // 2: CTA pairs (tcgen05 cta_group::2, cluster of two CTAs, each stages half of the weight rows)
     int halo = 0;  // 3x3 convs: 1 = row-halo A boxes (one per horizontal tap), 2 = one box for all nine taps; the packed weights use the matching K order
 };
@@ -359,14 +358,6 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    if (op.dbuf2) {
-        if (!(op.swa == 128 && op.block_n == 128 && op.halo == 1 && op.eg == 1)) return fail("two staging buffers: row-halo N = 128 kernel only");
-        if (op.ncta == 2) return launch_cg_pair<128, 128, 1, 1>(c, op, st);
-        launch_k(conv_gemm_kernel<128, 128, 1, 0, 1, 1>, op.grid, CgCfg<128, 128, 0, 1, 1>::THREADS, op.smem, st, op.p);
-        ++c->launches;
-        CUDA_OK(cudaGetLastError());
-        return 0;
-    }
     if (op.ncta == 2) {
         if (op.swa == 128 && op.block_n == 256 && op.halo == 0) return launch_cg_pair<128, 256, 0>(c, op, st);
         if (op.swa == 128 && op.block_n == 128 && op.halo == 0) return launch_cg_pair<128, 128, 0>(c, op, st);
@@ -466,7 +457,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 64, 3);
     SDN_SMEM_ATTR(128, 128, 0, 64);
     SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
-    SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 1, 1); SDN_SMEM_ATTR(128, 128, 1, 0, 2, 1);
+    SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2);
 #undef SDN_SMEM_ATTR
     {
         cudaLaunchConfig_t cfg = {};
@@ -768,12 +759,10 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     int k_total = 0;
     for (const SegSpec& sg : segs) k_total += aviews[sg.view].C * (op.halo ? 3 : 1);
     static const int cta2_min_kn = env_int("SDN_CTA2_MIN_KN", 512 * 256);
-    // row-halo N = 128 tiles with a short K loop (K = 576: 64 -> 128 forward, the 128-wide data gradient of a 64-channel
-    // layer): two staging buffers, and with them the pair form pays here too
-    static const int dbuf2_on = env_int("SDN_DBUF2", 1);
-    op.dbuf2 = dbuf2_on && op.halo == 1 && bn == 128 && op.swa == 128 && k_total <= 576 && !op.swd64;
+    // (measured and dropped: a second staging buffer for the K = 576 row-halo N = 128 layers - enc3.0 forward, dec2.0
+    // data gradient - changes nothing alone and the pair form stays 10-15 % slower there with it)
     if (cta2_on && bn >= 128 && op.halo <= 1 && !op.swd64 && op.swa == 128 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16) &&
-        ((long long)k_total * bn >= cta2_min_kn || op.dbuf2)) {
+        (long long)k_total * bn >= cta2_min_kn) {
         op.ncta = 2;
         p.tiles_n = (p.tiles_n + 1) / 2;   // the kernel walks pairs of image groups
     }
@@ -853,7 +842,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
         const int b_total = kblocks * 3 * bn_loc * op.swa;
         static const int ups_on = env_int("SDN_UPS", 3);
-        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes + (op.dbuf2 ? 128 * bn * 2 : 0);   // staging, scratch, barriers
+        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
         if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
         const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn_loc * op.swa);
