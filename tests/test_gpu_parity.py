@@ -231,6 +231,35 @@ def test_forward_eval_scaled_resolutions(dev, b, h, w):
     assert e_d <= 1e-2 and e_l <= 1e-2
 
 
+@pytest.mark.parametrize("b", [17, 19])
+def test_cta_pairs_odd_image_count(dev, b):
+    """The deep layers run as CTA pairs (tcgen05 cta_group::2): the two CTAs of a cluster take consecutive image
+    groups of one tile position, so with an ODD group count the last pair's second CTA works on an image past the
+    batch (TMA zero-fills its loads and clips its stores, its rows are excluded from the BatchNorm statistics).
+    Eval and train forward plus the train-mode BatchNorm buffers vs the fp32 oracle at such batches."""
+    h, w = 64, 96
+    model, sd = fresh_model(dev)
+    batch = make_batch(dev, b, h, w, seed=300 + b)
+    model.eval()
+    with torch.inference_mode():
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+    rd, rl = so.model_forward(sd, batch["input"], False, True)
+    assert (disp - rd).abs().max().item() / rd.abs().max().item() <= 1e-2
+    assert (logvar - rl).abs().max().item() / rl.abs().max().item() <= 1e-2
+    model.train()
+    with torch.no_grad():
+        disp, logvar = model(batch["input"], return_uncertainty=True)
+    bufs = {}
+    rd, rl = so.model_forward(sd, batch["input"], True, True, bufs)
+    e_d, e_l = rel(disp, rd), rel(logvar, rl)
+    print(f"train {b}x{h}x{w} (odd pair count) vs fp32 oracle, rel-L2: disparity {e_d:.2e} logvar {e_l:.2e}")
+    assert e_d <= 1e-2 and e_l <= 1.5e-2
+    after = model.state_dict()
+    for k, v in bufs.items():          # running statistics of every layer (the deep ones come from pair kernels)
+        if "running" in k:
+            assert rel(after[k], v.to(dev)) <= 2e-2, k
+
+
 def test_forward_train_batch32_full_resolution(dev):
     """The per-GPU batch of the 8-GPU run (32 x 240 x 320), train mode, vs the fp32 oracle on the same GPU."""
     model, sd = fresh_model(dev)
