@@ -185,7 +185,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>::TH
     using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>;
     constexpr int KB = Cfg::KB;
     constexpr bool PAIR = NCTA == 2;
-    static_assert(!PAIR || (HALO <= 1 && Cfg::EG == 1 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo kernels with N >= 128");
+    static_assert(!PAIR || (HALO <= 1 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo kernels with N >= 128");
     constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
     constexpr uint32_t SBO_A = 8 * SWA;
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(128 * NCTA, BLOCK_N, 0, 0);

@@ -352,8 +352,11 @@ static int launch_cg_pair(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
 }
 static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
     if (op.eg == 2 && op.block_n == 128) {
-        if (!(op.swa == 128 && op.halo == 0 && !op.swd64 && op.ncta == 1)) return fail("two epilogue groups at N = 128: plain kernel only");
-        launch_k(conv_gemm_kernel<128, 128, 0, 0, 1, 2>, op.grid, CgCfg<128, 128, 0, 1, 2>::THREADS, op.smem, st, op.p);
+        if (!(op.swa == 128 && op.halo <= 1 && !op.swd64)) return fail("two epilogue groups at N = 128: plain / row-halo kernels only");
+        if (op.halo == 1 && op.ncta == 2) return launch_cg_pair<128, 128, 1, 2>(c, op, st);
+        if (op.ncta == 2) return fail("two epilogue groups at N = 128: no pair form of the plain kernel");
+        if (op.halo == 1) launch_k(conv_gemm_kernel<128, 128, 1, 0, 1, 2>, op.grid, CgCfg<128, 128, 0, 1, 2>::THREADS, op.smem, st, op.p);
+        else launch_k(conv_gemm_kernel<128, 128, 0, 0, 1, 2>, op.grid, CgCfg<128, 128, 0, 1, 2>::THREADS, op.smem, st, op.p);
         ++c->launches;
         CUDA_OK(cudaGetLastError());
         return 0;
@@ -457,7 +460,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 64, 3);
     SDN_SMEM_ATTR(128, 128, 0, 64);
     SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
-    SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2);
+    SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2, 2);
 #undef SDN_SMEM_ATTR
     {
         cudaLaunchConfig_t cfg = {};
@@ -759,15 +762,23 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     int k_total = 0;
     for (const SegSpec& sg : segs) k_total += aviews[sg.view].C * (op.halo ? 3 : 1);
     static const int cta2_min_kn = env_int("SDN_CTA2_MIN_KN", 512 * 256);
-    // (measured and dropped: a second staging buffer for the K = 576 row-halo N = 128 layers - enc3.0 forward, dec2.0
-    // data gradient - changes nothing alone and the pair form stays 10-15 % slower there with it)
+    // Row-halo N = 128 tiles with K = 576 (enc3.0 forward, the 128-wide data gradient of dec2.0): one epilogue group
+    // needs longer for a 128 x 128 tile (TMEM loads, conversion, statistics, store) than the 36 MMAs of the main loop
+    // take, so these two layers were EPILOGUE-bound and the pair form alone made them 10-15 % slower; with TWO epilogue
+    // groups on alternate tiles AND the pair form (weights resident: 74 KB per CTA) they gain 15-20 %.  Measured
+    // beside it: two groups without the pair form change nothing, a second staging buffer alone changes nothing, and
+    // at K = 1152 two groups cost 7 % (fewer pipeline stages).  Not with CG_BSTATS: two groups' y tiles plus two
+    // staging buffers leave no room for the pipeline stages.
+    static const int eg2h_on = env_int("SDN_EG2_HALO", 1);
+    const bool eg2_halo = eg2h_on && cta2_on && op.halo == 1 && bn == 128 && op.swa == 128 && k_total <= 576 && !op.swd64 &&
+                          bs == nullptr && (p.tiles_n % 2 == 0 || p.tiles_n >= 16);
     if (cta2_on && bn >= 128 && op.halo <= 1 && !op.swd64 && op.swa == 128 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16) &&
-        (long long)k_total * bn >= cta2_min_kn) {
+        ((long long)k_total * bn >= cta2_min_kn || eg2_halo)) {
         op.ncta = 2;
         p.tiles_n = (p.tiles_n + 1) / 2;   // the kernel walks pairs of image groups
     }
     const int bn_loc = bn / op.ncta;       // weight rows this CTA stages
-    op.eg = (bn <= 64 || (short_k && bn == 128 && op.halo == 0 && op.ncta == 1)) ? 2 : 1;
+    op.eg = (bn <= 64 || (short_k && bn == 128 && op.halo == 0 && op.ncta == 1) || eg2_halo) ? 2 : 1;
     p.img_w = W; p.img_h = H; p.img_n = B;
     for (size_t i = 0; i < aviews.size(); ++i) {
         const SrcView& v = aviews[i];
@@ -842,7 +853,8 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         // three units per pipeline stage when >= 4 such stages still fit (fewer handshakes per tile)
         const int b_total = kblocks * 3 * bn_loc * op.swa;
         static const int ups_on = env_int("SDN_UPS", 3);
-        const int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;   // staging, scratch, barriers
+        const int fixed = (op.eg == 2 && bn == 128 ? CgCfg<128, 128, 0, 1, 2>::smem_bytes_halo(0, p.a_stage_bytes)
+                                                   : cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes)) + ybytes;   // staging, scratch, barriers
         const bool res = p.n_tiles == 1 && b_total <= bres_max;
         if (res) { p.flags |= CG_BRES; p.b_res_bytes = b_total; }
         const int unit_bytes = p.a_stage_bytes + (res ? 0 : 3 * bn_loc * op.swa);
@@ -850,6 +862,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
         p.ups = (ups_on == 3 && kblocks % 3 == 0 && budget / (3 * unit_bytes) >= 4) ? 3 : 1;
         stages = std::max(2, std::min(8, budget / (p.ups * unit_bytes)));
         op.smem = fixed + (res ? b_total : 0) + stages * p.ups * unit_bytes;
+        if (op.smem > 227 * 1024) return fail("build_gemm: row-halo shared memory %d", op.smem);
     } else {
         if (op.swd64) {
             while (stages > 2 && CgCfg<128, 128, 64>::smem_bytes(stages) > 220 * 1024) --stages;
