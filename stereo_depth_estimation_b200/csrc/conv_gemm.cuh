@@ -185,7 +185,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>::TH
     using Cfg = CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>;
     constexpr int KB = Cfg::KB;
     constexpr bool PAIR = NCTA == 2;
-    static_assert(!PAIR || (HALO <= 1 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo kernels with N >= 128");
+    static_assert(!PAIR || (HALO <= 2 && Cfg::NMMA == 1), "CTA pairs: plain / row-halo / box9 kernels");
     constexpr uint32_t LAYOUT_A = (SWA == 128) ? 2u : 4u;
     constexpr uint32_t SBO_A = 8 * SWA;
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(128 * NCTA, BLOCK_N, 0, 0);
@@ -299,8 +299,11 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>::TH
                             const bool noa = SDN_ABLATE(CG_DBG_NOLOADA);
                             if (sub == 0) ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                             if (ptx::elect_one()) {
-                                if (sub == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], uint32_t(ups) * (noa ? 0 : a_box));
-                                if (!noa)
+                                if (sub == 0 && tx_owner) ptx::mbar_arrive_expect_tx(&full_bar[s], uint32_t(NCTA * ups) * (noa ? 0 : a_box));
+                                if (PAIR)
+                                    ptx::tma_load_4d_pair(a_dst, &p.a_maps[seg.map], full_lead0 + uint32_t(s) * 8u, seg.c0 + cb * KB,
+                                                          x0 - 1, y0 - 1, n0);
+                                else if (!noa)
                                     ptx::tma_load_4d(a_dst, &p.a_maps[seg.map], &full_bar[s], seg.c0 + cb * KB, x0 - 1,
                                                      y0 - 1, n0);
                             }
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__((CgCfg<SWA, BLOCK_N, SWD_SEL, NCTA, EGSEL>::TH
                             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)
-                                    ptx::tc_mma_bf16_pred(
+                                    cg_mma<PAIR>(
                                         tmem_d, a0 + uint64_t(((tap / 3) * ROW_PITCH + (tap % 3) * SWA) / 16 + 2 * k),
                                         b0 + uint64_t(tap * Cfg::B_BYTES / 16 + 2 * k), IDESC,
                                         (tap | k) != 0 ? 1u : ((kb | j) != 0 ? 1u : 0u), lead);

@@ -365,6 +365,7 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
         if (op.swa == 128 && op.block_n == 256 && op.halo == 0) return launch_cg_pair<128, 256, 0>(c, op, st);
         if (op.swa == 128 && op.block_n == 128 && op.halo == 0) return launch_cg_pair<128, 128, 0>(c, op, st);
         if (op.swa == 128 && op.block_n == 128 && op.halo == 1) return launch_cg_pair<128, 128, 1>(c, op, st);
+        if (op.swa == 64 && op.block_n == 64 && op.halo == 2) return launch_cg_pair<64, 64, 2>(c, op, st);
         return fail("no CTA-pair conv_gemm instantiation for swizzle %d, BLOCK_N %d, halo %d", op.swa, op.block_n, op.halo);
     }
     if (op.swd64) {
@@ -461,6 +462,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 128, 0, 64);
     SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
     SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2, 2);
+    SDN_SMEM_ATTR(64, 64, 2, 0, 2);
 #undef SDN_SMEM_ATTR
     {
         cudaLaunchConfig_t cfg = {};
@@ -701,6 +703,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     Tile t = choose_tile(W, H, B, 128);
     static const int box9_on = env_int("SDN_BOX9", 1), bres_max = env_int("SDN_BRES_MAXKB", 80) * 1024;
     int smem_budget = 220 * 1024;
+    bool halfk = false;
     {
         // box9: one (TH+2)x(TW+2) box per (source, channel block) feeds all nine taps; needs the whole
         // packed weight matrix resident in shared memory and 8-pixel-wide tiles
@@ -725,6 +728,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
                 op.swa = 64;
                 op.halo = 2;
                 smem_budget = 226 * 1024;
+                halfk = true;
             }
         }
     }
@@ -772,8 +776,14 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     static const int eg2h_on = env_int("SDN_EG2_HALO", 1);
     const bool eg2_halo = eg2h_on && cta2_on && op.halo == 1 && bn == 128 && op.swa == 128 && k_total <= 576 && !op.swd64 &&
                           bs == nullptr && (p.tiles_n % 2 == 0 || p.tiles_n >= 16);
-    if (cta2_on && bn >= 128 && op.halo <= 1 && !op.swd64 && op.swa == 128 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16) &&
-        ((long long)k_total * bn >= cta2_min_kn || eg2_halo)) {
+    // box9 kernels in the pair form: measured on every box9 layer - the two half-k-block layers (128 -> 64: dec2.0
+    // forward, enc3.0 data gradient) gain 23-24 % (each CTA keeps half of the 147 KB weights, which leaves room for
+    // nine pipeline stages instead of three), every other box9 layer is unchanged (64 -> 64 forward) or 40-50 % SLOWER
+    // (the CG_BSTATS data gradients, the 32-channel-source kernels): pairs only where the weights do not fit otherwise
+    static const int box9_pair = env_int("SDN_BOX9_PAIRS", 1);
+    const bool pair_box9 = box9_pair && cta2_on && op.halo == 2 && halfk && bn == 64 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16);
+    if (pair_box9 || (cta2_on && bn >= 128 && op.halo <= 1 && !op.swd64 && op.swa == 128 && (p.tiles_n % 2 == 0 || p.tiles_n >= 16) &&
+        ((long long)k_total * bn >= cta2_min_kn || eg2_halo))) {
         op.ncta = 2;
         p.tiles_n = (p.tiles_n + 1) / 2;   // the kernel walks pairs of image groups
     }
@@ -833,7 +843,7 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
     if ((flags & CG_STATS) && (n_total > 512 || (p.n_tiles > 1 && bn < 128))) return fail("build_gemm: stats need n_total <= 512 and N tiles of >= 128 channels");
     int stages = 8;
     if (op.halo == 2) {
-        const int b_total = kblocks * 9 * bn * op.swa;
+        const int b_total = kblocks * 9 * bn_loc * op.swa;
         int fixed = cg_smem_halo(op.swa, bn, 0, p.a_stage_bytes) + ybytes;
         if (bs != nullptr && p.ybuf == 2 && (smem_budget - fixed - b_total) / p.a_stage_bytes < 3) {
             p.ybuf = 1;            // big resident weights (64 -> 64): keep three pipeline stages instead
