@@ -366,6 +366,7 @@ static int launch_cg(sdn_ctx* c, const GemmOp& op, cudaStream_t st) {
         if (op.swa == 128 && op.block_n == 128 && op.halo == 0) return launch_cg_pair<128, 128, 0>(c, op, st);
         if (op.swa == 128 && op.block_n == 128 && op.halo == 1) return launch_cg_pair<128, 128, 1>(c, op, st);
         if (op.swa == 64 && op.block_n == 64 && op.halo == 2) return launch_cg_pair<64, 64, 2>(c, op, st);
+        if (op.swa == 128 && op.block_n == 64 && op.halo == 2) return launch_cg_pair<128, 64, 2>(c, op, st);
         return fail("no CTA-pair conv_gemm instantiation for swizzle %d, BLOCK_N %d, halo %d", op.swa, op.block_n, op.halo);
     }
     if (op.swd64) {
@@ -462,7 +463,7 @@ static int set_smem_attrs() {
     SDN_SMEM_ATTR(128, 128, 0, 64);
     SDN_SMEM_ATTR(128, 256, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 0, 0, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2);
     SDN_SMEM_ATTR(128, 128, 0, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 1, 2); SDN_SMEM_ATTR(128, 128, 1, 0, 2, 2);
-    SDN_SMEM_ATTR(64, 64, 2, 0, 2);
+    SDN_SMEM_ATTR(64, 64, 2, 0, 2); SDN_SMEM_ATTR(128, 64, 2, 0, 2);
 #undef SDN_SMEM_ATTR
     {
         cudaLaunchConfig_t cfg = {};
@@ -724,7 +725,15 @@ static int build_gemm(sdn_ctx* c, GemmOp& op, int B, const std::vector<SrcView>&
             static const int half_on = env_int("SDN_BOX9_HALFK", 1), half_max = env_int("SDN_BOX9_HALFK_MAXKB", 150) * 1024;
             const int stage64 = (10 * 18 * 64 + 1023) & ~1023;
             const int need64 = cg_smem_halo(64, bn, 0, stage64) + 9 * cin_tot * bn * 2 + 3 * stage64;
-            if (half_on && 9 * cin_tot * bn * 2 <= half_max && need64 <= 226 * 1024) {
+            // a CTA pair keeps half of the weight rows per CTA: full 64-channel k-blocks fit again (two units of 36 MMAs
+            // per tile instead of four of 18, 128-byte TMA rows): dec2.0 forward 0.69 -> 0.62 ms over the half-k-block
+            // pair form; SDN_BOX9_PAIRS=2 keeps the half k-blocks
+            static const int pairfull = env_int("SDN_BOX9_PAIRS", 1) == 1 && env_int("SDN_CTA2", 1);
+            if (pairfull && bn == 64 && (B % 2 == 0 || B >= 16) && 9 * cin_tot * bn <= bres_max &&
+                cg_smem_halo(128, bn, 0, box9_stage) + 9 * cin_tot * bn + 3 * box9_stage <= 220 * 1024) {
+                op.halo = 2;
+                halfk = true;      // (selects the pair form below; the k-blocks stay whole)
+            } else if (half_on && 9 * cin_tot * bn * 2 <= half_max && need64 <= 226 * 1024) {
                 op.swa = 64;
                 op.halo = 2;
                 smem_budget = 226 * 1024;
